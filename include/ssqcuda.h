@@ -1,0 +1,196 @@
+/* ssqcuda.h -- C ABI of libssqcuda: the B200 (sm_100a) replacement for the
+ * compute path behind the reference's `ssqueeze._rs` pyo3 module.
+ *
+ * Drop-in boundary.  The reference's FFI for this path is the set of
+ * #[pyfunction]s registered in rust/src/lib.rs:23-35.  A maintainer keeps the
+ * pyo3 host crate and replaces each function body (everything inside
+ * `Python::allow_threads`) by one call into this library; INTEGRATION.md shows
+ * the `extern "C"` block and the rewritten bodies.  Each entry point below
+ * names the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; complex arrays are interleaved (re, im);
+ *  - every function returns an ssq_status; nothing throws or aborts across
+ *    the ABI; `ssq_last_error(ctx)` gives the message of the last failure on
+ *    that context (`ssq_last_error(NULL)`: last failure of a call that had no
+ *    context, thread-local);
+ *  - the caller allocates all outputs; sizes come from the *_shape queries;
+ *  - a context is bound to one CUDA device and is NOT thread-safe; use one
+ *    context per thread/device (the reference's functions are re-entrant and
+ *    release the GIL: stft.rs:37, ssq_stft.rs:122, cwt.rs:85, ssq_cwt.rs:329);
+ *  - `*_f64` entry points take/return HOST buffers with the reference's dtypes
+ *    (float64 / complex128); arithmetic on the device is fp32;
+ *  - `*_batch_f32` entry points take/return DEVICE (or pinned-host mapped)
+ *    buffers: x[channels, n] fp32 C-contiguous in, complex64 out
+ *    [channels, rows, cols]; they are asynchronous on the context's stream;
+ *  - `*_host_f32` entry points take HOST buffers (pinned preferred) and do the
+ *    host<->device copies themselves (synchronous at return);
+ *  - there is no CPU fallback: without a usable CUDA device every compute
+ *    call fails with SSQ_ECUDA.
+ */
+#ifndef SSQCUDA_H
+#define SSQCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssq_ctx ssq_ctx;
+
+typedef enum ssq_status {
+  SSQ_OK = 0,
+  SSQ_EINVAL = 1,        /* maps to PyValueError (ssq_stft.rs:96-101, cwt.rs:68-70) */
+  SSQ_ECUDA = 2,         /* CUDA runtime / launch failure, or no device */
+  SSQ_ENOMEM = 3,        /* device or host allocation failed */
+  SSQ_EUNSUPPORTED = 4,  /* valid in the reference, not built here (yet) */
+  SSQ_EPANIC = 5         /* input on which the reference panics (PanicException) */
+} ssq_status;
+
+/* padtype: the reference matches "reflect" | "zero" and silently falls back to
+ * reflect for anything else (stft.rs:25-29, ssq_stft.rs:124-128, cwt.rs:88-92) */
+enum { SSQ_PAD_REFLECT = 0, SSQ_PAD_ZERO = 1 };
+/* squeezing: "sum" | "lebesgue", fallback sum (ssq_stft.rs:292-296, ssq_cwt.rs:199-206) */
+enum { SSQ_SQUEEZE_SUM = 0, SSQ_SQUEEZE_LEBESGUE = 1 };
+/* wavelet: "morlet", anything else is GMW(gamma=3, beta=60) (cwt.rs:496-541) */
+enum { SSQ_WAVELET_GMW = 0, SSQ_WAVELET_MORLET = 1 };
+/* maprange: "maximal", anything else uses 1/scales (ssq_cwt.rs:450-461) */
+enum { SSQ_MAPRANGE_PEAK = 0, SSQ_MAPRANGE_MAXIMAL = 1 };
+/* ssq_freqs distribution: "linear", anything else log (ssq_cwt.rs:56-112) */
+enum { SSQ_FREQS_LOG = 0, SSQ_FREQS_LINEAR = 1 };
+
+/* flags (bit set) */
+enum {
+  SSQ_FLAG_MODULATED = 1u << 0,  /* ssq_stft: multiply Sx by exp(+2 pi i k (n_fft/2)/n_fft) before squeezing
+                                    (build-side extension needed by issq_stft) */
+  SSQ_FLAG_NO_FLIPUD = 1u << 1,  /* ssq_cwt: flipud=false (ssq_cwt.rs:180-184) */
+  SSQ_FLAG_L2_NORM = 1u << 2,    /* cwt: l1_norm=false -> multiply rows by sqrt(scale) (cwt.rs:253) */
+  SSQ_FLAG_RPADDED = 1u << 3,    /* cwt: return the padded [ns, pad_len] rows (cwt.rs:108-110) */
+  SSQ_FLAG_SIMD_SCALES = 1u << 4 /* cwt_simd default-scale generator (cwt_simd.rs:489-527) */
+};
+
+/* ---- library / context ------------------------------------------------- */
+/* replaces hello_from_bin (lib.rs:16-19): static identification string */
+const char* ssq_version(void);
+int ssq_device_count(void);
+ssq_status ssq_ctx_create(int device, ssq_ctx** out);
+void ssq_ctx_destroy(ssq_ctx* ctx);
+const char* ssq_last_error(const ssq_ctx* ctx);
+/* borrow a caller-owned cudaStream_t (NULL restores the context's own stream) */
+ssq_status ssq_ctx_set_stream(ssq_ctx* ctx, void* cuda_stream);
+ssq_status ssq_ctx_synchronize(ssq_ctx* ctx);
+/* number of kernels this context has launched since creation (bench "gpu_launches") */
+uint64_t ssq_ctx_launch_count(const ssq_ctx* ctx);
+/* device-time of the most recent batch call's dominant kernel, measured with
+ * CUDA events on the context's stream (ms); < 0 when not available */
+float ssq_ctx_last_kernel_ms(ssq_ctx* ctx);
+
+/* ---- shape queries ------------------------------------------------------ */
+/* stft.rs:32-34 / ssq_stft.rs:182-184: n_freqs = n_fft/2+1,
+ * n_frames = (n + n_fft-1 - n_fft)/hop + 1 = (n-1)/hop + 1 */
+ssq_status ssq_stft_shape(int64_t n, int n_fft, int hop, int64_t* n_freqs, int64_t* n_frames);
+/* cwt.rs:87,98 / ssq_cwt.rs:331,353: pad_len = next_pow2(n + n/2), n1 = (pad_len-n)/2 */
+ssq_status ssq_cwt_shape(int64_t n, int64_t* pad_len, int64_t* n1);
+/* cwt.rs:461-489 (and cwt_simd.rs:474-545 when simd != 0): returns the number
+ * of default scales; fills `scales` when non-NULL */
+int64_t ssq_cwt_default_scales(int64_t n, int nv, int simd, double* scales);
+
+/* ---- reference-typed entry points (host float64 / complex128) ----------- */
+/* replaces the body of `stft` (stft.rs:12-95).
+ * Sx: complex128 [n_freqs, n_frames] C-order; freqs: float64 [n_freqs]. */
+ssq_status ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n, int n_fft, int hop,
+                        const double* window, int64_t win_n, int padtype,
+                        double* Sx, double* freqs);
+
+/* replaces the body of `ssq_stft` (ssq_stft.rs:74-313).  n_fft<=0: min(n,512)
+ * (:92); win_len<=0: win_n (:93); gamma<0 or NaN: 10*EPS64 (:258-261).
+ * Tx: complex128 [n_freqs, n_frames]; ssq_freqs: float64 [n_freqs].
+ * Optional (may be NULL): Sx, dSx complex128 same shape; w float64 same shape
+ * (+inf where gated). */
+ssq_status ssq_ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n,
+                            const double* window, int64_t win_n, int n_fft, int win_len,
+                            int hop, double fs, int padtype, int squeezing, double gamma,
+                            unsigned flags, double* Tx, double* ssq_freqs,
+                            double* Sx, double* dSx, double* w);
+
+/* `istft`: absent from the Rust crate (lib.rs:25-32) but named by the north
+ * star; specified from old/ssqueezepy/_stft.py:184-256 in the Rust framing
+ * (unmodulated, pad offset (n_fft-1)/2).  Sx complex128 [n_freqs, n_frames]
+ * -> x float64 [n_out], n_out = N if N>0 else hop*n_frames. */
+ssq_status ssq_istft_f64(ssq_ctx* ctx, const double* Sx, int64_t n_freqs, int64_t n_frames,
+                         const double* window, int64_t win_n, int n_fft, int hop,
+                         int64_t N, int win_exp, double* x);
+
+/* `issq_stft` (old/ssqueezepy/_ssq_stft.py:139-198, full inverse; hop must be 1):
+ * y[j] = sum_k Re Tx[k,j] * 2 / (window_fit[n_fft/2] * fs). */
+ssq_status ssq_issq_stft_f64(ssq_ctx* ctx, const double* Tx, int64_t n_freqs, int64_t n_frames,
+                             const double* window, int64_t win_n, int n_fft, int hop,
+                             double fs, double* y);
+
+/* replaces the bodies of `cwt` / `cwt_simd` (cwt.rs:46-144, cwt_simd.rs:52-...).
+ * scales: float64 [ns] (caller passes the defaults from ssq_cwt_default_scales
+ * when the Python argument is None); dt from t[1]-t[0] | 1/fs | 1 (cwt.rs:66-76).
+ * Wx / dWx: complex128 [ns, n] (or [ns, pad_len] with SSQ_FLAG_RPADDED);
+ * dWx may be NULL (derivative=false). */
+ssq_status ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet,
+                       const double* scales, int64_t ns, double dt, int padtype,
+                       unsigned flags, double* Wx, double* dWx);
+
+/* replaces the body of `ssq_cwt` (ssq_cwt.rs:261-493).
+ * Tx complex128 [ns, n]; ssq_freqs float64 [ns] (not flipped, :482). */
+ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet,
+                           const double* scales, int64_t ns, double dt, int freq_dist,
+                           int padtype, int squeezing, int maprange, double gamma,
+                           unsigned flags, double* Tx, double* ssq_freqs);
+
+/* ---- batched throughput path (device buffers, fp32 / complex64) ---------- */
+/* replaces the per-channel Python loop around `_rs.ssq_stft`
+ * (tests/stft_ssq_test.py:230-251).  d_x: [channels, n] fp32 with row stride
+ * x_stride (elements).  d_Tx: complex64 [channels, n_freqs, n_frames].
+ * window is a HOST float64 array (fit to n_fft as ssq_stft.rs:104-119).
+ * Asynchronous on the context's stream. */
+ssq_status ssq_ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                  int64_t x_stride, const double* window, int64_t win_n,
+                                  int n_fft, int hop, double fs, int padtype, int squeezing,
+                                  double gamma, unsigned flags, float* d_Tx);
+/* same framing, output Sx (complex64 [channels, n_freqs, n_frames]); the
+ * window is used as given when win_n >= n_fft (first n_fft taps, stft_utils.rs:8) */
+ssq_status ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                              int64_t x_stride, const double* window, int64_t win_n,
+                              int n_fft, int hop, int padtype, float* d_Sx);
+/* d_Sx complex64 [channels, n_freqs, n_frames] -> d_xout fp32 [channels, n_out] */
+ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64_t channels,
+                               int64_t n_freqs, int64_t n_frames, const double* window,
+                               int64_t win_n, int n_fft, int hop, int64_t n_out, int win_exp,
+                               float* d_xout);
+ssq_status ssq_issq_stft_batch_f32(ssq_ctx* ctx, const float* d_Tx, int64_t channels,
+                                   int64_t n_freqs, int64_t n_frames, const double* window,
+                                   int64_t win_n, int n_fft, double fs, float* d_y);
+/* d_Wx / d_dWx complex64 [channels, ns, n] (d_dWx may be NULL) */
+ssq_status ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                             int64_t x_stride, int wavelet, const double* scales, int64_t ns,
+                             double dt, int padtype, unsigned flags, float* d_Wx, float* d_dWx);
+/* d_Tx complex64 [channels, ns, n]; ssq_freqs (host, float64 [ns]) may be NULL */
+ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                 int64_t x_stride, int wavelet, const double* scales,
+                                 int64_t ns, double dt, int freq_dist, int padtype,
+                                 int squeezing, int maprange, double gamma, unsigned flags,
+                                 float* d_Tx, double* ssq_freqs);
+
+/* ---- batched path with HOST buffers (copies inside; synchronous) --------- */
+/* x: host fp32 [channels, n]; Tx: host complex64 [channels, n_freqs, n_frames] */
+ssq_status ssq_ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_t channels, int64_t n,
+                                 const double* window, int64_t win_n, int n_fft, int hop,
+                                 double fs, int padtype, int squeezing, double gamma,
+                                 unsigned flags, float* Tx);
+
+/* pinned host memory helpers for the host-buffer path */
+ssq_status ssq_host_alloc(void** p, size_t bytes);
+void ssq_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSQCUDA_H */

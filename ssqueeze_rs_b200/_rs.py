@@ -1,0 +1,232 @@
+"""Host-side mirror of the reference's `ssqueeze._rs` module (rust/src/lib.rs:23-35):
+same callables, argument order, defaults, dtypes, return arity and error
+behaviour, each forwarding to one C-ABI call of libssqcuda (include/ssqcuda.h).
+
+The reference host layer is Rust/pyo3; no Rust toolchain exists in this image,
+so this module plays that role (INTEGRATION.md holds the pyo3 source a
+maintainer would compile instead).  Inputs must be 1-D float64 numpy arrays,
+as `PyReadonlyArray1<f64>` demands (anything else -> TypeError); outputs are
+freshly allocated C-contiguous complex128 / float64 arrays.
+
+Additions over the reference (north star): `istft`, `issq_stft`, and the
+keyword-only extras `modulated=` / `return_aux=` of `ssq_stft`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (FLAG_L2_NORM, FLAG_MODULATED, FLAG_NO_FLIPUD, FLAG_RPADDED, FLAG_SIMD_SCALES, PAD, SQUEEZE,
+                   default_context, load, raise_status)
+
+__all__ = ["hello_from_bin", "stft", "ssq_stft", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt"]
+
+
+def _f64_1d(a, name):
+    # PyReadonlyArray1<f64>: must already be a float64 ndarray of rank 1
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64 or a.ndim != 1:
+        raise TypeError(f"argument '{name}': expected a 1-D numpy.ndarray of float64, got "
+                        f"{type(a).__name__}" + (f" dtype={a.dtype} ndim={a.ndim}" if isinstance(a, np.ndarray) else ""))
+    return np.ascontiguousarray(a)  # strided views are copied (stft.rs:21-22 `.to_owned()`)
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def _str(v, name):
+    if not isinstance(v, str):
+        raise TypeError(f"argument '{name}': expected str")
+    return v
+
+
+def hello_from_bin() -> str:
+    """lib.rs:16-19."""
+    return load().ssq_version().decode()
+
+
+def stft(x, n_fft, hop_length, window, padtype):
+    """stft.rs:12-19: all five arguments required, positional or keyword.
+    Returns (Sx complex128 [n_fft//2+1, n_frames], freqs float64)."""
+    x = _f64_1d(x, "x")
+    window = _f64_1d(window, "window")
+    n_fft, hop = int(n_fft), int(hop_length)
+    if n_fft < 0 or hop < 0:
+        raise OverflowError("can't convert negative int to unsigned")  # usize extraction
+    ctx = default_context()
+    lib = load()
+    nfq, nfr = C.c_int64(), C.c_int64()
+    st = lib.ssq_stft_shape(len(x), n_fft, hop, C.byref(nfq), C.byref(nfr))
+    if st != _lib.SSQ_OK:
+        raise_status(st, None)
+    Sx = np.empty((nfq.value, nfr.value), dtype=np.complex128)
+    freqs = np.empty(nfq.value, dtype=np.float64)
+    st = lib.ssq_stft_f64(ctx.handle, _ptr(x), len(x), n_fft, hop, _ptr(window), len(window),
+                          PAD.get(_str(padtype, "padtype"), 0), _ptr(Sx), _ptr(freqs))
+    raise_status(st, ctx.handle)
+    return Sx, freqs
+
+
+def ssq_stft(x, window, n_fft=None, win_len=None, hop_len=1, fs=1.0, padtype="reflect", squeezing="sum",
+             gamma=None, *, modulated=False, return_aux=False):
+    """ssq_stft.rs:73-85.  Returns (Tx complex128 [n_freqs, n_frames], ssq_freqs).
+    `return_aux=True` appends a dict with Sx, dSx (complex128) and w (float64)."""
+    x = _f64_1d(x, "x")
+    window = _f64_1d(window, "window")
+    n = len(x)
+    nf = int(n_fft) if n_fft is not None else min(n, 512)  # ssq_stft.rs:92
+    wl = int(win_len) if win_len is not None else len(window)
+    hop = int(hop_len)
+    if nf < 0 or wl < 0 or hop < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    if wl > nf:  # ssq_stft.rs:96-101 (before any shape arithmetic)
+        raise ValueError(f"Window length {wl} cannot be greater than n_fft {nf}")
+    ctx = default_context()
+    lib = load()
+    nfq, nfr = C.c_int64(), C.c_int64()
+    st = lib.ssq_stft_shape(n, max(nf, 1), hop, C.byref(nfq), C.byref(nfr))
+    if st != _lib.SSQ_OK:
+        raise_status(st, None)
+    shape = (nf // 2 + 1, nfr.value)
+    Tx = np.empty(shape, dtype=np.complex128)
+    sf = np.empty(shape[0], dtype=np.float64)
+    Sx = dSx = w = None
+    if return_aux:
+        Sx = np.empty(shape, dtype=np.complex128)
+        dSx = np.empty(shape, dtype=np.complex128)
+        w = np.empty(shape, dtype=np.float64)
+    flags = FLAG_MODULATED if modulated else 0
+    g = float(gamma) if gamma is not None else -1.0
+    st = lib.ssq_ssq_stft_f64(ctx.handle, _ptr(x), n, _ptr(window), len(window), nf, wl, hop, float(fs),
+                              PAD.get(_str(padtype, "padtype"), 0), SQUEEZE.get(_str(squeezing, "squeezing"), 0),
+                              g, flags, _ptr(Tx), _ptr(sf), _ptr(Sx), _ptr(dSx), _ptr(w))
+    raise_status(st, ctx.handle)
+    if return_aux:
+        return Tx, sf, dict(Sx=Sx, dSx=dSx, w=w)
+    return Tx, sf
+
+
+def istft(Sx, window, n_fft=None, win_len=None, hop_len=1, N=None, win_exp=1):
+    """Inverse of `stft` (Rust framing).  Not in the Rust crate; specified from
+    old/ssqueezepy/_stft.py:184-256 with modulated=False and the Rust pad
+    offset (n_fft-1)//2."""
+    if not isinstance(Sx, np.ndarray) or Sx.ndim != 2 or Sx.dtype != np.complex128:
+        raise TypeError("argument 'Sx': expected a 2-D numpy.ndarray of complex128")
+    window = _f64_1d(window, "window")
+    Sx = np.ascontiguousarray(Sx)
+    nfq, nfr = Sx.shape
+    nf = int(n_fft) if n_fft else (nfq - 1) * 2
+    hop = int(hop_len)
+    n_out = int(N) if N else hop * nfr
+    if n_out < 1:
+        raise ValueError("N must be positive")
+    ctx = default_context()
+    x = np.empty(n_out, dtype=np.float64)
+    st = load().ssq_istft_f64(ctx.handle, _ptr(Sx), nfq, nfr, _ptr(window), len(window), nf, hop, n_out,
+                              int(win_exp), _ptr(x))
+    raise_status(st, ctx.handle)
+    return x
+
+
+def issq_stft(Tx, window, n_fft=None, win_len=None, hop_len=1, fs=1.0):
+    """Inverse synchrosqueezed STFT (old/ssqueezepy/_ssq_stft.py:139-198, full
+    inverse).  Needs hop_len == 1 and a Tx computed with `modulated=True`."""
+    if not isinstance(Tx, np.ndarray) or Tx.ndim != 2 or Tx.dtype != np.complex128:
+        raise TypeError("argument 'Tx': expected a 2-D numpy.ndarray of complex128")
+    window = _f64_1d(window, "window")
+    Tx = np.ascontiguousarray(Tx)
+    nfq, nfr = Tx.shape
+    nf = int(n_fft) if n_fft else (nfq - 1) * 2
+    ctx = default_context()
+    y = np.empty(nfr, dtype=np.float64)
+    st = load().ssq_issq_stft_f64(ctx.handle, _ptr(Tx), nfq, nfr, _ptr(window), len(window), nf, int(hop_len),
+                                  float(fs), _ptr(y))
+    raise_status(st, ctx.handle)
+    return y
+
+
+def _dt(fs, t):
+    # cwt.rs:66-76 / ssq_cwt.rs:283-293
+    if t is not None:
+        t = _f64_1d(t, "t")
+        if len(t) < 2:
+            raise ValueError("Time vector must have at least 2 elements")
+        return float(t[1] - t[0])
+    if fs is not None:
+        return 1.0 / float(fs)
+    return 1.0
+
+
+def _scales(scales, n, nv, simd):
+    if scales is not None:
+        return _f64_1d(scales, "scales").copy()
+    lib = load()
+    ns = lib.ssq_cwt_default_scales(n, int(nv), int(simd), C.c_void_p(0))
+    out = np.empty(max(ns, 0), dtype=np.float64)
+    if ns > 0:
+        lib.ssq_cwt_default_scales(n, int(nv), int(simd), _ptr(out))
+    return out
+
+
+def _cwt_impl(x, wavelet, scales, fs, t, nv, l1_norm, derivative, padtype, rpadded, simd):
+    x = _f64_1d(x, "x")
+    n = len(x)
+    dt = _dt(fs, t)
+    sc = _scales(scales, n, nv, simd)
+    ns = len(sc)
+    lib = load()
+    pl, n1 = C.c_int64(), C.c_int64()
+    st = lib.ssq_cwt_shape(n, C.byref(pl), C.byref(n1))
+    if st != _lib.SSQ_OK:
+        raise_status(st, None)
+    cols = pl.value if rpadded else n
+    Wx = np.empty((ns, cols), dtype=np.complex128)
+    dWx = np.empty((ns, cols), dtype=np.complex128) if derivative else None
+    flags = (0 if l1_norm else FLAG_L2_NORM) | (FLAG_RPADDED if rpadded else 0) | (FLAG_SIMD_SCALES if simd else 0)
+    ctx = default_context()
+    if ns > 0:
+        st = lib.ssq_cwt_f64(ctx.handle, _ptr(x), n, 1 if _str(wavelet, "wavelet") == "morlet" else 0, _ptr(sc), ns,
+                             dt, PAD.get(_str(padtype, "padtype"), 0), flags, _ptr(Wx), _ptr(dWx))
+        raise_status(st, ctx.handle)
+    return Wx, sc, dWx
+
+
+def cwt(x, wavelet="gmw", scales=None, fs=None, t=None, nv=32, l1_norm=True, derivative=False,
+        padtype="reflect", rpadded=False, vectorized=True, patience=0):
+    """cwt.rs:32-60.  Always a 3-tuple (Wx, scales, dWx | None).  `vectorized`
+    selects parallel vs serial code in the reference (same numbers) and
+    `patience` is ignored there; both are accepted and ignored here."""
+    return _cwt_impl(x, wavelet, scales, fs, t, nv, l1_norm, derivative, padtype, rpadded, simd=False)
+
+
+def cwt_simd(x, wavelet="gmw", scales=None, fs=None, t=None, nv=32, l1_norm=True, derivative=False,
+             padtype="reflect", rpadded=False, vectorized=True, patience=0):
+    """cwt_simd.rs:38-66: `cwt` with the exp(p*ln2) default-scale generator."""
+    return _cwt_impl(x, wavelet, scales, fs, t, nv, l1_norm, derivative, padtype, rpadded, simd=True)
+
+
+def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=32, padtype="reflect",
+            squeezing="sum", maprange="peak", difftype="trig", gamma=None, vectorized=True, flipud=True):
+    """ssq_cwt.rs:245-277.  Returns (Tx complex128 [n_scales, N], ssq_freqs).
+    `difftype` / `vectorized` are ignored as in the reference (:296-297)."""
+    x = _f64_1d(x, "x")
+    n = len(x)
+    dt = _dt(fs, t)
+    sc = _scales(scales, n, nv, False)
+    ns = len(sc)
+    if ns < 1:
+        raise _lib.PanicException("no scales: index out of bounds at ssq_cwt.rs:459")
+    dist = 1 if (ssq_freqs is not None and _str(ssq_freqs, "ssq_freqs") == "linear") else 0
+    Tx = np.empty((ns, n), dtype=np.complex128)
+    sf = np.empty(ns, dtype=np.float64)
+    ctx = default_context()
+    g = float(gamma) if gamma is not None else -1.0
+    st = load().ssq_ssq_cwt_f64(ctx.handle, _ptr(x), n, 1 if _str(wavelet, "wavelet") == "morlet" else 0, _ptr(sc),
+                                ns, dt, dist, PAD.get(_str(padtype, "padtype"), 0),
+                                SQUEEZE.get(_str(squeezing, "squeezing"), 0),
+                                1 if _str(maprange, "maprange") == "maximal" else 0, g,
+                                0 if flipud else FLAG_NO_FLIPUD, _ptr(Tx), _ptr(sf))
+    raise_status(st, ctx.handle)
+    return Tx, sf

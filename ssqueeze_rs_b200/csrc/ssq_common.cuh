@@ -1,0 +1,135 @@
+// ssq_common.cuh -- context object, error plumbing and small device helpers
+// shared by every kernel file of libssqcuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+#include <math.h>
+#include "../../include/ssqcuda.h"
+
+#define SSQ_PI 3.14159265358979323846
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+// One context = one device + one stream + grow-only workspaces + table cache.
+struct ssq_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int max_smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  uint64_t launches = 0;
+  std::string err;
+  // workspaces
+  DevBuf ws_in, ws_out, ws_aux0, ws_aux1, ws_aux2, ws_fft0, ws_fft1, ws_misc;
+  // STFT table cache (window / diff-window / twiddles on device)
+  DevBuf tab;
+  std::vector<double> tab_window;  // fitted window the tables were built from
+  int tab_nfft = -1;
+  int tab_kind = -1;
+  double tab_sscale = 1.0;
+  // CWT twiddle cache
+  DevBuf cwt_tw;
+  int64_t cwt_tw_n = -1;
+  DevBuf cwt_scales;
+};
+
+static thread_local std::string g_tls_err;
+
+static inline ssq_status ssq_fail(ssq_ctx* ctx, ssq_status st, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_tls_err = buf;
+  return st;
+}
+
+#define SSQ_CUDA_TRY(ctx, expr)                                                      \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess)                                                           \
+      return ssq_fail((ctx), _e == cudaErrorMemoryAllocation ? SSQ_ENOMEM : SSQ_ECUDA, \
+                      "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define SSQ_TRY(expr)                      \
+  do {                                     \
+    ssq_status _s = (expr);                \
+    if (_s != SSQ_OK) return _s;           \
+  } while (0)
+
+static inline ssq_status devbuf_reserve(ssq_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return SSQ_OK;
+  if (b.p) {
+    // the old buffer may still be in use by work queued on the stream
+    SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes < 256 ? 256 : bytes;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    (void)cudaGetLastError();
+    return ssq_fail(ctx, SSQ_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return SSQ_OK;
+}
+
+static inline ssq_status ssq_check_launch(ssq_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return ssq_fail(ctx, SSQ_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  ctx->launches++;
+  return SSQ_OK;
+}
+
+// ---- device helpers -------------------------------------------------------
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// Padded-signal sample fetch in the reference's STFT framing
+// (stft_utils.rs:19-65): padded index p, left = (n_fft-1)/2.
+__device__ __forceinline__ float stft_sample(const float* __restrict__ x, int64_t n, int64_t p,
+                                             int left, int padtype) {
+  int64_t o = p - left;
+  if (o >= 0 && o < n) return __ldg(x + o);
+  if (padtype == SSQ_PAD_ZERO) return 0.f;
+  if (o < 0) {
+    int64_t m = -o;  // stft_utils.rs:34-36
+    return m < n ? __ldg(x + m) : 0.f;
+  }
+  int64_t m = 2 * n - 2 - o;  // stft_utils.rs:42-44
+  return (m >= 0 && m < n) ? __ldg(x + m) : 0.f;
+}
+
+// Non-atomic-free float2 accumulate in shared memory: fp32 shared atomics are
+// CAS loops on sm_100a (ATOMS.CAST.SPIN), so do one 64-bit CAS for the pair.
+__device__ __forceinline__ void smem_add_f2(float2* addr, float re, float im) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *p, assumed;
+  do {
+    assumed = old;
+    float2 v;
+    v.x = __uint_as_float((unsigned)(assumed & 0xffffffffull)) + re;
+    v.y = __uint_as_float((unsigned)(assumed >> 32)) + im;
+    unsigned long long nv = ((unsigned long long)__float_as_uint(v.y) << 32) | __float_as_uint(v.x);
+    old = atomicCAS(p, assumed, nv);
+  } while (old != assumed);
+}

@@ -1,0 +1,687 @@
+// ssqcuda.cu -- C ABI of libssqcuda (see include/ssqcuda.h) and the host-side
+// set-up logic of each transform.  Device code lives in the *.cuh files.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared
+#include "ssq_common.cuh"
+#include "host_math.h"
+#include "stft_kernels.cuh"
+#include "stft_fast.cuh"
+#include "cwt_kernels.cuh"
+
+#include <algorithm>
+#include <new>
+
+static const double kEps64 = 2.2204460492503131e-16;
+
+// ===========================================================================
+// library / context
+// ===========================================================================
+extern "C" const char* ssq_version(void) {
+  return "ssqcuda 0.1 (B200 sm_100a; stft, ssq_stft, istft, issq_stft, cwt, cwt_simd, ssq_cwt)";
+}
+
+extern "C" int ssq_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" ssq_status ssq_ctx_create(int device, ssq_ctx** out) {
+  if (!out) return ssq_fail(nullptr, SSQ_EINVAL, "ssq_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    return ssq_fail(nullptr, SSQ_ECUDA, "no CUDA device available (%s); libssqcuda has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n)
+    return ssq_fail(nullptr, SSQ_EINVAL, "device %d out of range [0, %d)", device, n);
+  ssq_ctx* c = new (std::nothrow) ssq_ctx();
+  if (!c) return ssq_fail(nullptr, SSQ_ENOMEM, "out of host memory");
+  c->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete c;
+    return ssq_fail(nullptr, SSQ_ECUDA, "cudaSetDevice/GetDeviceProperties: %s", cudaGetErrorString(e));
+  }
+  if (prop.major < 10) {
+    delete c;
+    return ssq_fail(nullptr, SSQ_ECUDA, "device %d is sm_%d%d; libssqcuda is built for sm_100a only", device,
+                    prop.major, prop.minor);
+  }
+  c->num_sms = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+    delete c;
+    return ssq_fail(nullptr, SSQ_ECUDA, "stream/event creation: %s", cudaGetErrorString(e));
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return SSQ_OK;
+}
+
+extern "C" void ssq_ctx_destroy(ssq_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->ws_in, &ctx->ws_out, &ctx->ws_aux0, &ctx->ws_aux1, &ctx->ws_aux2, &ctx->ws_fft0,
+                    &ctx->ws_fft1, &ctx->ws_misc, &ctx->tab, &ctx->cwt_tw, &ctx->cwt_scales};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char* ssq_last_error(const ssq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_tls_err.c_str(); }
+
+extern "C" ssq_status ssq_ctx_set_stream(ssq_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_ctx_synchronize(ssq_ctx* ctx) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return SSQ_OK;
+}
+
+extern "C" uint64_t ssq_ctx_launch_count(const ssq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" float ssq_ctx_last_kernel_ms(ssq_ctx* ctx) {
+  if (!ctx || !ctx->ev_valid) return -1.f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+extern "C" ssq_status ssq_host_alloc(void** p, size_t bytes) {
+  if (!p) return ssq_fail(nullptr, SSQ_EINVAL, "p is NULL");
+  cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    *p = nullptr;
+    return ssq_fail(nullptr, SSQ_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+  }
+  return SSQ_OK;
+}
+extern "C" void ssq_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ===========================================================================
+// shape queries
+// ===========================================================================
+extern "C" ssq_status ssq_stft_shape(int64_t n, int n_fft, int hop, int64_t* n_freqs, int64_t* n_frames) {
+  if (n < 1 || n_fft < 1 || hop < 1)
+    return ssq_fail(nullptr, SSQ_EPANIC, "stft shape: n=%lld n_fft=%d hop=%d (the reference panics: stft.rs:33)",
+                    (long long)n, n_fft, hop);
+  if (n_freqs) *n_freqs = n_fft / 2 + 1;
+  if (n_frames) *n_frames = (n - 1) / hop + 1;
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_cwt_shape(int64_t n, int64_t* pad_len, int64_t* n1) {
+  if (n < 1) return ssq_fail(nullptr, SSQ_EINVAL, "cwt shape: n=%lld", (long long)n);
+  const int64_t pl = ssqhost::next_power_of_2(n + n / 2);
+  if (pad_len) *pad_len = pl;
+  if (n1) *n1 = (pl - n) / 2;
+  return SSQ_OK;
+}
+
+extern "C" int64_t ssq_cwt_default_scales(int64_t n, int nv, int simd, double* scales) {
+  return ssqhost::default_scales(n, nv, simd, scales);
+}
+
+// ===========================================================================
+// STFT family: host set-up
+// ===========================================================================
+enum { TAB_SSQ = 0, TAB_STFT = 1, TAB_ISTFT = 2 };
+
+struct StftTables {
+  const float* win;
+  const float* dwin;
+  const float2* tw;
+  const float* wa;
+  const float* wpow;
+  double s_scale;
+};
+
+// Uploads (or reuses) the per-window device tables:
+// [win N][dwin*s N][tw 2N][wa N][wpow N] floats.
+static ssq_status stft_tables(ssq_ctx* ctx, const std::vector<double>& wfit, int kind, int win_exp,
+                              StftTables* T) {
+  const int N = (int)wfit.size();
+  const int key_kind = kind * 16 + (kind == TAB_ISTFT ? (win_exp & 15) : 0);
+  const bool hit = ctx->tab.p && ctx->tab_nfft == N && ctx->tab_kind == key_kind &&
+                   ctx->tab_window.size() == wfit.size() &&
+                   memcmp(ctx->tab_window.data(), wfit.data(), sizeof(double) * N) == 0;
+  float* base = nullptr;
+  if (!hit) {
+    std::vector<float> h((size_t)6 * N, 0.f);
+    double s_scale = 1.0;
+    for (int i = 0; i < N; ++i) h[i] = (float)wfit[i];
+    if (kind == TAB_SSQ) {
+      std::vector<double> dw = ssqhost::diff_window(wfit);
+      double sw = 0.0, sd = 0.0;
+      for (int i = 0; i < N; ++i) {
+        sw += wfit[i] * wfit[i];
+        sd += dw[i] * dw[i];
+      }
+      if (sd > 0.0 && sw > 0.0) s_scale = std::sqrt(sw / sd);
+      for (int i = 0; i < N; ++i) h[(size_t)N + i] = (float)(dw[i] * s_scale);
+    }
+    for (int i = 0; i < N; ++i) {
+      const double ang = -2.0 * SSQ_PI * (double)i / (double)N;
+      h[(size_t)2 * N + 2 * i] = (float)std::cos(ang);
+      h[(size_t)2 * N + 2 * i + 1] = (float)std::sin(ang);
+    }
+    if (kind == TAB_ISTFT) {
+      for (int i = 0; i < N; ++i) {
+        const double wa = win_exp == 0 ? 1.0 : std::pow(wfit[i], (double)win_exp);
+        h[(size_t)4 * N + i] = (float)(wa / (double)N);
+        h[(size_t)5 * N + i] = (float)std::pow(wfit[i], (double)(win_exp + 1));
+      }
+    }
+    SSQ_TRY(devbuf_reserve(ctx, ctx->tab, h.size() * sizeof(float)));
+    // the previous tables may still be read by queued kernels
+    SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->tab.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->tab_window = wfit;
+    ctx->tab_nfft = N;
+    ctx->tab_kind = key_kind;
+    ctx->tab_sscale = s_scale;
+  }
+  base = (float*)ctx->tab.p;
+  T->win = base;
+  T->dwin = base + N;
+  T->tw = (const float2*)(base + 2 * (size_t)N);
+  T->wa = base + 4 * (size_t)N;
+  T->wpow = base + 5 * (size_t)N;
+  T->s_scale = ctx->tab_sscale;
+  return SSQ_OK;
+}
+
+static inline int ilog2_exact(int n) {
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return ((1 << l) == n) ? l : -1;
+}
+
+struct TilePlan {
+  int F, acc_stride, nw;
+  size_t smem;
+  int grid;
+};
+
+// tile geometry for the generic (shared-memory) kernels
+static ssq_status plan_generic_tiles(ssq_ctx* ctx, int n_fft, int n_freqs, int64_t n_frames, int channels,
+                                     TilePlan* tp, int64_t* tiles_per_channel, int64_t* total_tiles) {
+  const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin, 200 * 1024);
+  const int acc_stride = n_freqs | 1;
+  int F = 32, nw = 8;
+  auto need = [&](int F_, int nw_) {
+    return ((size_t)F_ * acc_stride + (size_t)nw_ * 2 * n_fft + (size_t)n_fft) * sizeof(float2);
+  };
+  while (nw > 1 && need(F, nw) > budget) nw >>= 1;
+  while (F > 1 && need(F, nw) > budget) F >>= 1;
+  if (need(F, nw) > budget)
+    return ssq_fail(ctx, SSQ_EUNSUPPORTED, "n_fft=%d needs %zu B of shared memory per CTA (> %zu)", n_fft,
+                    need(F, nw), budget);
+  if ((int64_t)F > n_frames) {
+    int f2 = 1;
+    while (f2 < n_frames) f2 <<= 1;
+    F = std::max(1, std::min(F, f2));
+  }
+  tp->F = F;
+  tp->acc_stride = acc_stride;
+  tp->nw = nw;
+  tp->smem = need(F, nw);
+  *tiles_per_channel = (n_frames + F - 1) / F;
+  *total_tiles = *tiles_per_channel * channels;
+  const int per_sm = std::max<int>(1, (int)(((size_t)220 * 1024) / (tp->smem + 1024)));
+  const int64_t g = std::min<int64_t>(*total_tiles, (int64_t)ctx->num_sms * per_sm);
+  tp->grid = (int)std::max<int64_t>(1, g);
+  return SSQ_OK;
+}
+
+struct StftCall {
+  int mode;  // 0 ssq, 1 stft
+  const float* d_x;
+  int64_t channels, n, x_stride;
+  std::vector<double> wfit;
+  int n_fft, hop;
+  double fs;
+  int padtype, squeezing;
+  double gamma;
+  unsigned flags;
+  float2* d_out;
+  float2* aux_Sx;
+  float2* aux_dSx;
+  float* aux_w;
+};
+
+static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int N = c.n_fft;
+  if (N < 2) return ssq_fail(ctx, SSQ_EINVAL, "n_fft=%d: need n_fft >= 2", N);
+  if (c.hop < 1) return ssq_fail(ctx, SSQ_EPANIC, "hop=%d: the reference divides by it (ssq_stft.rs:183)", c.hop);
+  if (c.n < 1 || c.channels < 1)
+    return ssq_fail(ctx, SSQ_EPANIC, "empty input (n=%lld, channels=%lld): usize underflow in the reference",
+                    (long long)c.n, (long long)c.channels);
+  const int n_freqs = N / 2 + 1;
+  const int64_t n_frames = (c.n - 1) / c.hop + 1;
+  StftTables T;
+  SSQ_TRY(stft_tables(ctx, c.wfit, c.mode == 0 ? TAB_SSQ : TAB_STFT, 0, &T));
+
+  StftParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = c.d_x;
+  P.x_stride = c.x_stride;
+  P.n = c.n;
+  P.channels = (int)c.channels;
+  P.n_fft = N;
+  P.hop = c.hop;
+  P.n_freqs = n_freqs;
+  P.log2n = ilog2_exact(N);
+  P.is_pow2 = P.log2n >= 0;
+  P.n_frames = n_frames;
+  P.left = (N - 1) / 2;
+  P.padtype = c.padtype == SSQ_PAD_ZERO ? SSQ_PAD_ZERO : SSQ_PAD_REFLECT;
+  P.win = T.win;
+  P.dwin = T.dwin;
+  P.tw = T.tw;
+  const double dw_f = 0.5 * c.fs / ((double)n_freqs - 1.0);  // ssq_stft.rs:50,273
+  const double gamma = (c.gamma >= 0.0) ? c.gamma : 10.0 * kEps64;  // NaN compares false -> default
+  P.cphase = (float)(((double)n_freqs - 1.0) / (SSQ_PI * T.s_scale));
+  P.gate2 = (float)(4.0 * gamma * gamma);
+  P.tx_scale = (float)(0.5 * dw_f);
+  P.leb_val = (float)(dw_f / (double)n_freqs);
+  P.dw_f = (float)dw_f;
+  P.dsx_scale = (float)(0.5 * c.fs / T.s_scale);
+  P.mode = c.mode;
+  P.squeezing = c.squeezing == SSQ_SQUEEZE_LEBESGUE ? SSQ_SQUEEZE_LEBESGUE : SSQ_SQUEEZE_SUM;
+  P.modulated = (c.flags & SSQ_FLAG_MODULATED) ? 1 : 0;
+  P.out = c.d_out;
+  P.aux_Sx = c.aux_Sx;
+  P.aux_dSx = c.aux_dSx;
+  P.aux_w = c.aux_w;
+
+  const bool want_aux = c.aux_Sx || c.aux_dSx || c.aux_w;
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  bool done = false;
+  if (!want_aux) {
+    ssq_status st = stft_fast_launch(ctx, P, &done);
+    if (st != SSQ_OK) return st;
+  }
+  if (!done) {
+    TilePlan tp;
+    SSQ_TRY(plan_generic_tiles(ctx, N, n_freqs, n_frames, (int)c.channels, &tp, &P.tiles_per_channel,
+                               &P.total_tiles));
+    P.F = tp.F;
+    P.acc_stride = tp.acc_stride;
+    SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)tp.smem));
+    stft_generic_kernel<<<tp.grid, tp.nw * 32, tp.smem, ctx->stream>>>(P);
+    SSQ_TRY(ssq_check_launch(ctx, "stft_generic_kernel"));
+  }
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  return SSQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batched device entry points
+// ---------------------------------------------------------------------------
+extern "C" ssq_status ssq_ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                             int64_t x_stride, const double* window, int64_t win_n, int n_fft,
+                                             int hop, double fs, int padtype, int squeezing, double gamma,
+                                             unsigned flags, float* d_Tx) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!d_x || !d_Tx || !window || win_n < 1) return ssq_fail(ctx, SSQ_EINVAL, "NULL/empty argument");
+  if (n_fft <= 0) n_fft = (int)std::min<int64_t>(n, 512);  // ssq_stft.rs:92
+  if (win_n > n_fft)
+    return ssq_fail(ctx, SSQ_EINVAL, "Window length %lld cannot be greater than n_fft %d", (long long)win_n, n_fft);
+  StftCall c;
+  c.mode = 0;
+  c.d_x = d_x;
+  c.channels = channels;
+  c.n = n;
+  c.x_stride = x_stride > 0 ? x_stride : n;
+  c.wfit = ssqhost::fit_window(window, win_n, n_fft);
+  c.n_fft = n_fft;
+  c.hop = hop;
+  c.fs = fs;
+  c.padtype = padtype;
+  c.squeezing = squeezing;
+  c.gamma = gamma;
+  c.flags = flags;
+  c.d_out = (float2*)d_Tx;
+  c.aux_Sx = nullptr;
+  c.aux_dSx = nullptr;
+  c.aux_w = nullptr;
+  return run_stft_family(ctx, c);
+}
+
+extern "C" ssq_status ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                         int64_t x_stride, const double* window, int64_t win_n, int n_fft,
+                                         int hop, int padtype, float* d_Sx) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!d_x || !d_Sx || !window) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  if (n_fft < 2) return ssq_fail(ctx, SSQ_EINVAL, "n_fft=%d: need n_fft >= 2", n_fft);
+  if (win_n < n_fft)
+    return ssq_fail(ctx, SSQ_EPANIC,
+                    "window length %lld < n_fft %d: the reference panics in rustfft (stft_utils.rs:8, stft.rs:67)",
+                    (long long)win_n, n_fft);
+  StftCall c;
+  c.mode = 1;
+  c.d_x = d_x;
+  c.channels = channels;
+  c.n = n;
+  c.x_stride = x_stride > 0 ? x_stride : n;
+  c.wfit.assign(window, window + n_fft);  // first n_fft taps (stft_utils.rs:8)
+  c.n_fft = n_fft;
+  c.hop = hop;
+  c.fs = 1.0;
+  c.padtype = padtype;
+  c.squeezing = SSQ_SQUEEZE_SUM;
+  c.gamma = 0.0;
+  c.flags = 0;
+  c.d_out = (float2*)d_Sx;
+  c.aux_Sx = nullptr;
+  c.aux_dSx = nullptr;
+  c.aux_w = nullptr;
+  return run_stft_family(ctx, c);
+}
+
+extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64_t channels, int64_t n_freqs,
+                                          int64_t n_frames, const double* window, int64_t win_n, int n_fft,
+                                          int hop, int64_t n_out, int win_exp, float* d_xout) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!d_Sx || !d_xout || !window || win_n < 1) return ssq_fail(ctx, SSQ_EINVAL, "NULL/empty argument");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_fft <= 0) n_fft = (int)(n_freqs - 1) * 2;  // _stft.py:229
+  if (n_fft < 2 || n_fft / 2 + 1 != n_freqs)
+    return ssq_fail(ctx, SSQ_EINVAL, "Sx has %lld rows but n_fft=%d needs %d", (long long)n_freqs, n_fft,
+                    n_fft / 2 + 1);
+  if (hop < 1 || n_frames < 1 || channels < 1 || win_exp < 0)
+    return ssq_fail(ctx, SSQ_EINVAL, "bad hop/n_frames/channels/win_exp");
+  if (n_out <= 0) n_out = (int64_t)hop * n_frames;  // _stft.py:231
+  std::vector<double> wfit = ssqhost::fit_window(window, win_n, n_fft);
+  StftTables T;
+  SSQ_TRY(stft_tables(ctx, wfit, TAB_ISTFT, win_exp, &T));
+  const int64_t L = n_out + n_fft - 1;
+  const int64_t max_hops = (L - n_fft) / hop + 1;
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_misc, (size_t)channels * L * sizeof(float)));
+  SSQ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_misc.p, 0, (size_t)channels * L * sizeof(float), ctx->stream));
+
+  IstftParams P;
+  memset(&P, 0, sizeof(P));
+  P.Sx = (const float2*)d_Sx;
+  P.channels = (int)channels;
+  P.n_fft = n_fft;
+  P.hop = hop;
+  P.n_freqs = (int)n_freqs;
+  P.log2n = ilog2_exact(n_fft);
+  P.is_pow2 = P.log2n >= 0;
+  P.n_frames = n_frames;
+  P.n_use = std::min<int64_t>(n_frames, max_hops);
+  P.L = L;
+  P.wa = T.wa;
+  P.tw = T.tw;
+  P.xacc = (float*)ctx->ws_misc.p;
+  TilePlan tp;
+  SSQ_TRY(plan_generic_tiles(ctx, n_fft, (int)n_freqs, P.n_use, (int)channels, &tp, &P.tiles_per_channel,
+                             &P.total_tiles));
+  P.F = tp.F;
+  P.acc_stride = tp.acc_stride;
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  SSQ_CUDA_TRY(ctx,
+               cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
+  istft_ola_kernel<<<tp.grid, tp.nw * 32, tp.smem, ctx->stream>>>(P);
+  SSQ_TRY(ssq_check_launch(ctx, "istft_ola_kernel"));
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  dim3 g((unsigned)((n_out + 255) / 256), (unsigned)channels);
+  istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
+                                                    (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+  SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_issq_stft_batch_f32(ssq_ctx* ctx, const float* d_Tx, int64_t channels, int64_t n_freqs,
+                                              int64_t n_frames, const double* window, int64_t win_n, int n_fft,
+                                              double fs, float* d_y) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!d_Tx || !d_y || !window || win_n < 1) return ssq_fail(ctx, SSQ_EINVAL, "NULL/empty argument");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_fft <= 0) n_fft = (int)(n_freqs - 1) * 2;
+  if (n_fft < 2 || n_fft / 2 + 1 != n_freqs)
+    return ssq_fail(ctx, SSQ_EINVAL, "Tx has %lld rows but n_fft=%d needs %d", (long long)n_freqs, n_fft,
+                    n_fft / 2 + 1);
+  if (n_frames < 1 || channels < 1) return ssq_fail(ctx, SSQ_EINVAL, "empty Tx");
+  std::vector<double> wfit = ssqhost::fit_window(window, win_n, n_fft);
+  const double wc = wfit[(size_t)(n_fft / 2)];
+  const float scale = (float)(2.0 / (wc * fs));
+  dim3 g((unsigned)((n_frames + 255) / 256), (unsigned)channels);
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  issq_stft_kernel<<<g, 256, 0, ctx->stream>>>((const float2*)d_Tx, n_freqs, n_frames, scale, d_y);
+  SSQ_TRY(ssq_check_launch(ctx, "issq_stft_kernel"));
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  return SSQ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// reference-typed entry points (host f64 / c128)
+// ---------------------------------------------------------------------------
+static ssq_status upload_f64_as_f32(ssq_ctx* ctx, const double* x, size_t n, DevBuf& buf) {
+  std::vector<float> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = (float)x[i];
+  SSQ_TRY(devbuf_reserve(ctx, buf, n * sizeof(float)));
+  SSQ_CUDA_TRY(ctx, cudaMemcpyAsync(buf.p, h.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h goes out of scope
+  return SSQ_OK;
+}
+
+static ssq_status download_f32_as_f64(ssq_ctx* ctx, const void* d, size_t n, double* out) {
+  std::vector<float> h(n);
+  SSQ_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n; ++i) out[i] = (double)h[i];
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n, int n_fft, int hop,
+                                   const double* window, int64_t win_n, int padtype, double* Sx, double* freqs) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!x || !window || !Sx) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int64_t n_freqs, n_frames;
+  if (ssq_stft_shape(n, n_fft, hop, &n_freqs, &n_frames) != SSQ_OK)
+    return ssq_fail(ctx, SSQ_EPANIC, "%s", g_tls_err.c_str());
+  SSQ_TRY(upload_f64_as_f32(ctx, x, (size_t)n, ctx->ws_in));
+  const size_t cnt = (size_t)n_freqs * n_frames;
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, cnt * sizeof(float2)));
+  SSQ_TRY(ssq_stft_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, n, n, window, win_n, n_fft, hop, padtype,
+                             (float*)ctx->ws_out.p));
+  SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_out.p, cnt * 2, Sx));
+  if (freqs) {
+    // Array1::linspace(0.0, 0.5, n_freqs) (stft.rs:40)
+    const double step = n_freqs > 1 ? 0.5 / (double)(n_freqs - 1) : 0.0;
+    for (int64_t i = 0; i < n_freqs; ++i) freqs[i] = step * (double)i;
+    if (n_freqs > 1) freqs[n_freqs - 1] = 0.5;
+  }
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n, const double* window,
+                                       int64_t win_n, int n_fft, int win_len, int hop, double fs, int padtype,
+                                       int squeezing, double gamma, unsigned flags, double* Tx, double* ssq_freqs,
+                                       double* Sx, double* dSx, double* w) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!x || !window || !Tx || win_n < 1) return ssq_fail(ctx, SSQ_EINVAL, "NULL/empty argument");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n < 1) return ssq_fail(ctx, SSQ_EPANIC, "empty x: usize underflow at ssq_stft.rs:183");
+  if (n_fft <= 0) n_fft = (int)std::min<int64_t>(n, 512);
+  if (win_len <= 0) win_len = (int)win_n;
+  if (win_len > n_fft)
+    return ssq_fail(ctx, SSQ_EINVAL, "Window length %d cannot be greater than n_fft %d", win_len, n_fft);
+  if (hop < 1) return ssq_fail(ctx, SSQ_EPANIC, "hop_len=%d: division by zero at ssq_stft.rs:183", hop);
+  if (n_fft < 2) return ssq_fail(ctx, SSQ_EINVAL, "n_fft=%d: need n_fft >= 2", n_fft);
+  const int64_t n_freqs = n_fft / 2 + 1, n_frames = (n - 1) / hop + 1;
+  const size_t cnt = (size_t)n_freqs * n_frames;
+  SSQ_TRY(upload_f64_as_f32(ctx, x, (size_t)n, ctx->ws_in));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, cnt * sizeof(float2)));
+  StftCall c;
+  c.mode = 0;
+  c.d_x = (const float*)ctx->ws_in.p;
+  c.channels = 1;
+  c.n = n;
+  c.x_stride = n;
+  c.wfit = ssqhost::fit_window(window, win_n, n_fft);
+  c.n_fft = n_fft;
+  c.hop = hop;
+  c.fs = fs;
+  c.padtype = padtype;
+  c.squeezing = squeezing;
+  c.gamma = gamma;
+  c.flags = flags;
+  c.d_out = (float2*)ctx->ws_out.p;
+  c.aux_Sx = nullptr;
+  c.aux_dSx = nullptr;
+  c.aux_w = nullptr;
+  if (Sx) {
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, cnt * sizeof(float2)));
+    c.aux_Sx = (float2*)ctx->ws_aux0.p;
+  }
+  if (dSx) {
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux1, cnt * sizeof(float2)));
+    c.aux_dSx = (float2*)ctx->ws_aux1.p;
+  }
+  if (w) {
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux2, cnt * sizeof(float)));
+    c.aux_w = (float*)ctx->ws_aux2.p;
+  }
+  SSQ_TRY(run_stft_family(ctx, c));
+  SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_out.p, cnt * 2, Tx));
+  if (Sx) SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_aux0.p, cnt * 2, Sx));
+  if (dSx) SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_aux1.p, cnt * 2, dSx));
+  if (w) SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_aux2.p, cnt, w));
+  if (ssq_freqs)  // ssq_stft.rs:42-54
+    for (int64_t i = 0; i < n_freqs; ++i) ssq_freqs[i] = (double)i * 0.5 * fs / ((double)n_freqs - 1.0);
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_istft_f64(ssq_ctx* ctx, const double* Sx, int64_t n_freqs, int64_t n_frames,
+                                    const double* window, int64_t win_n, int n_fft, int hop, int64_t N,
+                                    int win_exp, double* x) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!Sx || !window || !x) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_freqs < 2 || n_frames < 1 || hop < 1) return ssq_fail(ctx, SSQ_EINVAL, "bad Sx shape / hop");
+  const int64_t n_out = N > 0 ? N : (int64_t)hop * n_frames;
+  const size_t cnt = (size_t)n_freqs * n_frames;
+  SSQ_TRY(upload_f64_as_f32(ctx, Sx, cnt * 2, ctx->ws_in));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, (size_t)n_out * sizeof(float)));
+  SSQ_TRY(ssq_istft_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, n_freqs, n_frames, window, win_n, n_fft, hop,
+                              n_out, win_exp, (float*)ctx->ws_out.p));
+  return download_f32_as_f64(ctx, ctx->ws_out.p, (size_t)n_out, x);
+}
+
+extern "C" ssq_status ssq_issq_stft_f64(ssq_ctx* ctx, const double* Tx, int64_t n_freqs, int64_t n_frames,
+                                        const double* window, int64_t win_n, int n_fft, int hop, double fs,
+                                        double* y) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!Tx || !window || !y) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  if (hop != 1) return ssq_fail(ctx, SSQ_EINVAL, "inversion with `hop_len != 1` is unsupported.");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_freqs < 2 || n_frames < 1) return ssq_fail(ctx, SSQ_EINVAL, "bad Tx shape");
+  const size_t cnt = (size_t)n_freqs * n_frames;
+  SSQ_TRY(upload_f64_as_f32(ctx, Tx, cnt * 2, ctx->ws_in));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, (size_t)n_frames * sizeof(float)));
+  SSQ_TRY(ssq_issq_stft_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, n_freqs, n_frames, window, win_n, n_fft, fs,
+                                  (float*)ctx->ws_out.p));
+  return download_f32_as_f64(ctx, ctx->ws_out.p, (size_t)n_frames, y);
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer batched path: chunked over channels, copies overlapped with
+// compute on three streams (H2D | kernel | D2H).
+// ---------------------------------------------------------------------------
+extern "C" ssq_status ssq_ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_t channels, int64_t n,
+                                            const double* window, int64_t win_n, int n_fft, int hop, double fs,
+                                            int padtype, int squeezing, double gamma, unsigned flags, float* Tx) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!x || !Tx || !window) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_fft <= 0) n_fft = (int)std::min<int64_t>(n, 512);
+  int64_t n_freqs, n_frames;
+  if (ssq_stft_shape(n, n_fft, hop, &n_freqs, &n_frames) != SSQ_OK)
+    return ssq_fail(ctx, SSQ_EPANIC, "%s", g_tls_err.c_str());
+  const size_t out_per_ch = (size_t)n_freqs * n_frames * sizeof(float2);
+  const size_t in_per_ch = (size_t)n * sizeof(float);
+  // chunk so that two output chunks stay below ~8 GiB of device memory
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(((size_t)4 << 30) / std::max<size_t>(1, out_per_ch)));
+  chunk = std::min(chunk, channels);
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_in, 2 * chunk * in_per_ch));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, 2 * chunk * out_per_ch));
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t e_in[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
+  SSQ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  SSQ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e_k[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e_out[i], cudaEventDisableTiming);
+  }
+  ssq_status st = SSQ_OK;
+  int it = 0;
+  for (int64_t c0 = 0; c0 < channels && st == SSQ_OK; c0 += chunk, ++it) {
+    const int b = it & 1;
+    const int64_t cc = std::min(chunk, channels - c0);
+    float* din = (float*)ctx->ws_in.p + (size_t)b * chunk * n;
+    char* dout = (char*)ctx->ws_out.p + (size_t)b * chunk * out_per_ch;
+    // the kernel that last read this input slot / the copy that last drained this output slot
+    if (it >= 2) {
+      cudaStreamWaitEvent(s_in, e_k[b], 0);
+      cudaStreamWaitEvent(ctx->stream, e_out[b], 0);
+    }
+    cudaMemcpyAsync(din, x + (size_t)c0 * n, (size_t)cc * in_per_ch, cudaMemcpyHostToDevice, s_in);
+    cudaEventRecord(e_in[b], s_in);
+    cudaStreamWaitEvent(ctx->stream, e_in[b], 0);
+    st = ssq_ssq_stft_batch_f32(ctx, din, cc, n, n, window, win_n, n_fft, hop, fs, padtype, squeezing, gamma,
+                                flags, (float*)dout);
+    if (st != SSQ_OK) break;
+    cudaEventRecord(e_k[b], ctx->stream);
+    cudaStreamWaitEvent(s_out, e_k[b], 0);
+    cudaMemcpyAsync((char*)Tx + (size_t)c0 * out_per_ch, dout, (size_t)cc * out_per_ch, cudaMemcpyDeviceToHost,
+                    s_out);
+    cudaEventRecord(e_out[b], s_out);
+  }
+  cudaStreamSynchronize(s_in);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(s_out);
+  cudaError_t e = cudaGetLastError();
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(e_in[i]);
+    cudaEventDestroy(e_k[i]);
+    cudaEventDestroy(e_out[i]);
+  }
+  cudaStreamDestroy(s_in);
+  cudaStreamDestroy(s_out);
+  if (st != SSQ_OK) return st;
+  if (e != cudaSuccess) return ssq_fail(ctx, SSQ_ECUDA, "host-buffer pipeline: %s", cudaGetErrorString(e));
+  return SSQ_OK;
+}
+
+#include "cwt_host.inl"

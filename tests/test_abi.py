@@ -1,0 +1,82 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol
+include/ssqcuda.h declares; compute calls fail loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ssqcuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built_lib):
+    from ssqueeze_rs_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} declared in ssqcuda.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_version_and_shapes(built_lib):
+    from ssqueeze_rs_b200 import _rs
+    assert "ssqcuda" in _rs.hello_from_bin()
+    a, b = ctypes.c_int64(), ctypes.c_int64()
+    assert built_lib.ssq_stft_shape(1000, 256, 64, ctypes.byref(a), ctypes.byref(b)) == 0
+    assert (a.value, b.value) == (129, 16)  # tests/stft_test.py expected shape
+    assert built_lib.ssq_stft_shape(1000, 256, 0, ctypes.byref(a), ctypes.byref(b)) != 0  # hop 0 panics upstream
+    assert built_lib.ssq_cwt_shape(1000, ctypes.byref(a), ctypes.byref(b)) == 0
+    assert (a.value, b.value) == (2048, 524)
+    assert built_lib.ssq_cwt_shape(1 << 20, ctypes.byref(a), ctypes.byref(b)) == 0
+    assert a.value == 1 << 21
+    ns = built_lib.ssq_cwt_default_scales(1 << 20, 32, 0, None)
+    assert ns == 576  # BASELINE config 3
+
+
+def test_default_scales_match_oracle(built_lib):
+    from oracle import ssq_oracle as O
+    for simd in (0, 1):
+        ns = built_lib.ssq_cwt_default_scales(1000, 16, simd, None)
+        out = np.empty(ns)
+        built_lib.ssq_cwt_default_scales(1000, 16, simd, out.ctypes.data)
+        assert np.allclose(out, O.generate_log_scales(1000, 16, simd=bool(simd)), rtol=1e-14)
+
+
+def test_argument_validation_without_gpu(built_lib):
+    from ssqueeze_rs_b200 import _rs
+    x = np.zeros(100)
+    with pytest.raises(TypeError):
+        _rs.stft(x.astype(np.float32), 16, 4, np.ones(16), "reflect")  # PyReadonlyArray1<f64>
+    with pytest.raises(TypeError):
+        _rs.ssq_stft([0.0] * 10, np.ones(4))
+    with pytest.raises(ValueError):
+        _rs.ssq_stft(x, np.ones(32), n_fft=16)  # ssq_stft.rs:96-101, raised before any device work
+    with pytest.raises(ValueError):
+        _rs.cwt(x, t=np.array([0.0]))  # cwt.rs:68-70
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device every compute entry point must raise, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ssqueeze_rs_b200 import _rs, SsqError
+    with pytest.raises(SsqError):
+        _rs.ssq_stft(np.zeros(64), np.ones(16), n_fft=16)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ssqueeze_rs_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl")):
+                s = open(os.path.join(dp, f)).read()
+                assert "oracle" not in s.replace("no Python/NumPy fallback", ""), f"{f} mentions the oracle"

@@ -1,0 +1,107 @@
+"""CPU: the oracle against the committed golden vectors (tests/golden/*.npz,
+made by tests/golden/make_golden.py from the vendored upstream implementation)
+and against the reference's documented quirks."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ssq_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_oracle_matches_upstream_golden():
+    z = np.load(os.path.join(G, "upstream_odd.npz"))
+    for ci, (N, n_fft, hop) in enumerate(z["cases"]):
+        p = f"c{ci}_"
+        x, win = z[p + "x"], z[p + "window"]
+        Tx, sf, aux = O.ssq_stft(x, win, n_fft=int(n_fft), hop_len=int(hop), fs=1.0, return_aux=True)
+        assert Tx.shape == z[p + "Tx"].shape
+        sc = np.abs(z[p + "Tx"]).max()
+        assert np.abs(Tx - z[p + "Tx"]).max() <= 1e-12 * sc
+        assert np.abs(aux["Sx"] - z[p + "Sx"]).max() <= 1e-12 * np.abs(z[p + "Sx"]).max()
+        assert np.abs(aux["dSx"] - z[p + "dSx"]).max() <= 1e-11 * np.abs(z[p + "dSx"]).max()
+        assert np.allclose(sf, z[p + "ssq_freqs"], rtol=1e-13, atol=0)
+        Sx, _ = O.stft(x, int(n_fft), int(hop), win, "reflect")
+        xr = O.istft(Sx, win, n_fft=int(n_fft), hop_len=int(hop), N=int(N))
+        assert np.abs(xr - z[p + "istft"]).max() < 1e-13
+        assert np.abs(xr - x).mean() < 1e-14  # old/tests/reconstruction_test.py:165,179
+
+
+def test_oracle_readme_regression():
+    z = np.load(os.path.join(G, "readme_cases.npz"))
+    x = z["x"]
+    win = np.hanning(256)
+    Sx, freqs = O.stft(x, 256, 64, win, "reflect")
+    assert Sx.shape == (129, 16) and freqs.shape == (129,)  # tests/stft_test.py:137-151
+    assert np.array_equal(Sx, z["stft_Sx"])
+    Tx, sf = O.ssq_stft(x, win, n_fft=256, hop_len=64, fs=1000.0)
+    assert Tx.shape == (129, 16)
+    assert np.allclose(Tx, z["ssq_stft_Tx"], rtol=1e-12, atol=1e-12)
+    Tq, sfq = O.ssq_cwt(x, "gmw", z["scales"], fs=1000.0, nv=16)
+    assert Tq.shape == (32, 1000)  # tests/ssq_cwt_test.py:19-57
+    assert np.allclose(np.abs(Tq).sum(axis=1), z["ssq_cwt_gmw_Tx_abs_rowsum"], rtol=1e-9)
+
+
+def test_pad_conventions():
+    x = np.arange(1.0, 11.0)
+    p = O.pad_reflect_stft(x, 6)  # pad 5: left 2, right 3 (stft_utils.rs:21-23)
+    assert list(p[:2]) == [3.0, 2.0] and list(p[-3:]) == [9.0, 8.0, 7.0]
+    assert len(p) == 15
+    # pad longer than the signal: remainder stays zero (guards :35, :43)
+    q = O.pad_reflect_stft(np.array([1.0, 2.0, 3.0]), 12)
+    assert len(q) == 14
+    left = 5
+    assert list(q[left:left + 3]) == [1.0, 2.0, 3.0]
+    assert list(q[:left]) == [0.0, 0.0, 0.0, 3.0, 2.0]
+    assert list(q[left + 3:]) == [2.0, 1.0, 0.0, 0.0, 0.0, 0.0]
+    z = O.pad_zeros_stft(x, 6)
+    assert z[:2].sum() == 0 and z[-3:].sum() == 0
+
+
+def test_diff_window_and_fit():
+    w = np.hanning(64)
+    dw = O.diff_window(w)
+    # derivative of a smooth window: antisymmetric-ish, zero mean
+    assert abs(dw.sum()) < 1e-12
+    num = np.gradient(w)
+    assert np.abs(dw[4:-4] - num[4:-4]).max() < 2e-3
+    assert O.fit_window(np.ones(4), 8).tolist() == [0, 0, 1, 1, 1, 1, 0, 0]
+    assert O.fit_window(np.arange(8.0), 4).tolist() == [2, 3, 4, 5]
+
+
+def test_reassign_ties_and_clamp():
+    # a w value exactly between two grid points goes to the LOWER index
+    # (strict '<', ssq_stft.rs:285); out of range clamps; NaN -> bin 0
+    sf = O.ssq_freqs_stft(5, 8.0)  # 0,1,2,3,4
+    Sx = np.ones((5, 1), dtype=np.complex128)
+    w = np.array([[1.5], [100.0], [np.nan], [np.inf], [2.49]])
+    Tx, kk = O.reassign_stft(Sx, w, sf, "sum")
+    assert kk[:, 0].tolist() == [1, 4, 0, -1, 2]
+    assert Tx[:, 0].real.tolist() == [1.0, 1.0, 1.0, 0.0, 1.0]
+
+
+def test_cwt_quirks():
+    assert O.next_power_of_2(1500) == 2048 and O.next_power_of_2(1024) == 1024
+    xi = O.xifn(1.0, 8)
+    assert xi[4] > 0 and xi[5] < 0  # Nyquist positive (wavelets/base.rs:23-30)
+    s = O.generate_log_scales(1000, 16)
+    assert len(s) == int(np.ceil((np.log2(500.0) - 1) * 16)) and abs(s[0] - 2.0) < 1e-15
+    s2 = O.generate_log_scales(1000, 16, simd=True)
+    assert np.allclose(s, s2, rtol=1e-14)
+    # default nv=32 grid has ratio 2^(1/32) < 1.1 -> binned LINEARLY (ssq_cwt.rs:135-139)
+    x = np.sin(2 * np.pi * 100 * np.linspace(0, 1, 1000, endpoint=False))
+    Tx, sf, aux = O.ssq_cwt(x, "gmw", None, fs=1000.0, nv=32, maprange="maximal", return_aux=True)
+    assert Tx.shape == (len(aux["scales"]), 1000)
+    assert sf[1] / sf[0] < 1.1
+    Wx, sc, dWx = O.cwt(x, "morlet", np.logspace(1, 5, 32) / 1000, fs=1000.0, nv=16)
+    assert Wx.shape == (32, 1000) and dWx is None  # 3-tuple always (cwt.rs:60,143)
+
+
+def test_error_behaviour():
+    x = np.zeros(10)
+    with pytest.raises(ValueError):
+        O.ssq_stft(x, np.ones(16), n_fft=8)  # win_len > n_fft (ssq_stft.rs:96-101)
+    with pytest.raises(ValueError):
+        O.cwt(x, t=np.array([0.0]))  # cwt.rs:68-70
