@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- ssq_stft input Msamples/s on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A step = one pass of the fused ssq_stft kernel over one batch of synthetic
+multichannel input.  N=1 workload = BASELINE.json configs[1]: 384 channels x
+60 s @ 30 kHz (1.8 M samples), n_fft=512, hop=32, Hann window, reflect pad.
+N>1: every rank processes its own 384-channel batch (channels are independent
+units; no data-path collective) -> weak scaling; value = all ranks' samples /
+max-over-ranks device time.
+
+`value`  : inputs already resident in HBM, device time by CUDA events.
+`e2e`    : same metric through the C ABI with HOST (pinned) buffers, H2D and
+           D2H copies of every byte inside the timed region.
+`--impl reference`: the reference's own algorithm on the host cores (the C
+           restatement oracle/ssq_stft_ref.c, as-written variant; the Rust
+           crate cannot be built in this image), rank 0 only, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FS = 30000.0
+N_FFT, HOP = 512, 32
+CHANNELS = 384
+SAMPLES = 1_800_000
+WORKLOAD = "ssq_stft 384ch x 1.8M samples (60 s @ 30 kHz) synthetic neural, n_fft=512 hop=32 hann reflect"
+# measured once with `ncu --set full` (profiles/), per launch of the dominant kernel; None until captured
+NCU_DRAM_BYTES_PER_LAUNCH = None
+
+
+def algorithmic_bytes(channels, n, n_fft=N_FFT, hop=HOP):
+    """B = C*(4*N + 8*n_freqs*n_frames)."""
+    n_freqs, n_frames = n_fft // 2 + 1, (n - 1) // hop + 1
+    return channels * (4 * n + 8 * n_freqs * n_frames)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_neural(torch, channels, n, fs, device, seed):
+    """SURVEY 8(d) 'neural' recipe, generated on the device: 50*pink(0.5-300 Hz) +
+    20*sin(2pi 8 t + phi) + 10*sin(2pi (40 + 20 sin 2pi 0.2 t) t) + 5*sin(2pi 60 t) +
+    10*N(0,1) + Poisson(20 Hz) biphasic 1.5 ms spikes of 80-200 uV."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    x = torch.empty((channels, n), dtype=torch.float32, device=device)
+    t = torch.arange(n, device=device, dtype=torch.float64) / fs
+    base = (10.0 * torch.sin(2 * np.pi * (40.0 + 20.0 * torch.sin(2 * np.pi * 0.2 * t)) * t)
+            + 5.0 * torch.sin(2 * np.pi * 60.0 * t)).to(torch.float32)
+    freqs = torch.fft.rfftfreq(n, d=1.0 / fs).to(device)
+    shape = torch.where((freqs >= 0.5) & (freqs <= 300.0), 1.0 / torch.sqrt(torch.clamp(freqs, min=0.5)),
+                        torch.zeros_like(freqs)).to(torch.float32)
+    L = int(0.0015 * fs)
+    tt = torch.arange(L, device=device, dtype=torch.float32) / L
+    templ = (torch.sin(2 * np.pi * tt) * torch.hann_window(L, device=device)).view(1, 1, L)
+    step = 16
+    for c0 in range(0, channels, step):
+        c1 = min(channels, c0 + step)
+        m = c1 - c0
+        white = torch.randn((m, n), generator=g, device=device, dtype=torch.float32)
+        pink = torch.fft.irfft(torch.fft.rfft(white) * shape, n=n)
+        pink = pink / pink.std(dim=1, keepdim=True).clamp_min(1e-12)
+        phi = torch.rand((m, 1), generator=g, device=device, dtype=torch.float64) * 2 * np.pi
+        theta = torch.sin(2 * np.pi * 8.0 * t.view(1, -1) + phi).to(torch.float32)
+        spikes = (torch.rand((m, n), generator=g, device=device) < (20.0 / fs)).to(torch.float32)
+        amp = 80.0 + 120.0 * torch.rand((m, n), generator=g, device=device)
+        sp = torch.nn.functional.conv1d((spikes * amp).view(m, 1, n), templ, padding=L // 2)[:, 0, :n]
+        x[c0:c1] = (50.0 * pink + 20.0 * theta + base.view(1, -1)
+                    + 10.0 * torch.randn((m, n), generator=g, device=device) + sp)
+        del white, pink, theta, spikes, amp, sp
+    return x
+
+
+def make_neural_cpu(channels, n, fs, seed):
+    """Same recipe on the host (numpy) for the CPU reference arm's bounded sample."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    out = np.empty((channels, n))
+    f = np.fft.rfftfreq(n, 1.0 / fs)
+    shape = np.where((f >= 0.5) & (f <= 300.0), 1.0 / np.sqrt(np.maximum(f, 0.5)), 0.0)
+    for c in range(channels):
+        pink = np.fft.irfft(np.fft.rfft(rng.standard_normal(n)) * shape, n=n)
+        pink /= max(pink.std(), 1e-12)
+        sp = np.zeros(n)
+        idx = np.nonzero(rng.random(n) < 20.0 / fs)[0]
+        L = int(0.0015 * fs)
+        templ = np.sin(2 * np.pi * np.arange(L) / L) * np.hanning(L)
+        for i in idx:
+            a = 80 + 120 * rng.random()
+            e = min(n, i + L)
+            sp[i:e] += a * templ[:e - i]
+        out[c] = (50 * pink + 20 * np.sin(2 * np.pi * 8 * t + rng.random() * 2 * np.pi)
+                  + 10 * np.sin(2 * np.pi * (40 + 20 * np.sin(2 * np.pi * 0.2 * t)) * t)
+                  + 5 * np.sin(2 * np.pi * 60 * t) + 10 * rng.standard_normal(n) + sp)
+    return out
+
+
+def cpu_reference_run(n_samples, steps, warmup, mode=0, channels=1):
+    """Times the C restatement (oracle/ssq_stft_ref.c) on `channels` x n_samples."""
+    from oracle import cref
+    x = make_neural_cpu(channels, n_samples, FS, 0x5351)
+    w = np.hanning(N_FFT)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for c in range(channels):
+            cref.ssq_stft(x[c], w, N_FFT, HOP, FS, mode=mode)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return channels * n_samples / (sum(times) / len(times)) / 1e6, cref.num_threads(), sum(times) / len(times)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_s = 450_000
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 3))
+    msps, threads, sec = cpu_reference_run(n_s, steps, warm, mode=0)
+    line = {
+        "impl": "reference", "metric": "ssq_stft input Msamples/s", "value": msps, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_fft": N_FFT, "hop": HOP, "fs": FS},
+        "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                         "sample": f"1 channel x {n_s} samples per step of the same synthetic recipe; C restatement "
+                                   "of ssq_stft.rs as written (frames parallel with a plan per frame, serial phase, "
+                                   "serial O(n_freqs^2) arg-min reassignment); OpenMP threads = host cores"},
+        "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ssqueeze_rs_b200 import _lib
+    from ssqueeze_rs_b200.batch import Engine
+
+    channels, n = args.channels, args.samples
+    n_freqs, n_frames = N_FFT // 2 + 1, (n - 1) // HOP + 1
+    eng = Engine(local_rank)
+    window = np.hanning(N_FFT)
+    x = make_neural(torch, channels, n, FS, dev, 0x5351 + rank)
+    Tx = torch.empty((channels, n_freqs, n_frames), dtype=torch.complex64, device=dev)
+    torch.cuda.synchronize()
+    eng.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def step():
+        eng.ssq_stft_ptr(x.data_ptr(), channels, n, window, N_FFT, HOP, FS, Tx.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+        kernel_ms.append(eng.ctx.last_kernel_ms())
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = eng.ctx.launch_count() - launches0
+    total_ms = ev0.elapsed_time(ev1)
+    tms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    total_ms = float(tms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * channels * n / (ms_per_step * 1e-3) / 1e6
+
+    # checksum so the timed work cannot be optimised away / silently skipped
+    chk = float(torch.view_as_real(Tx[0, :, :64]).abs().sum().item())
+    if not np.isfinite(chk) or chk == 0.0:
+        raise SystemExit("bench.py: kernel produced no output")
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations) -----------
+    peak, peak_src = measured_peak_gbs()
+    kms = float(np.mean(kernel_ms))
+    abytes = algorithmic_bytes(channels, n)
+    achieved = abytes / (kms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel_ms": kms, "algorithmic_bytes_per_launch": abytes,
+                "peak_source": peak_src, "kernel": eng.last_kernel_name()}
+
+    # ---- e2e through the host-buffer C-ABI call --------------------------------
+    del Tx
+    torch.cuda.empty_cache()
+    e2e = run_e2e(eng, args, rank, world, window, x, dev)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        msps, threads, sec = cpu_reference_run(900_000, 1, 0, mode=0)
+        msps_i, _, sec_i = cpu_reference_run(900_000, 1, 1, mode=1, channels=2)
+        cpu_baseline = {"value": msps, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                        "sample": f"1 channel x 900000 samples ({sec:.1f} s), C restatement of ssq_stft.rs as written",
+                        "as_intended_value": msps_i,
+                        "as_intended_note": "same numerics, shared FFT plan, O(1) binning, parallel phase/reassign; "
+                                            f"2 channels x 900000 samples ({sec_i:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": "ssq_stft input Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "channels_per_gpu": channels, "samples_per_channel": n, "n_fft": N_FFT,
+                       "hop": HOP, "fs": FS, "parallelism": f"channel-shard x{world}, no collective",
+                       "l2_policy": "inputs (2.8 GB) and outputs (44 GB) per step exceed the 126 MB L2; no flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "checksum": chk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(eng, args, rank, world, window, x_dev, dev):
+    """Host pinned x -> [H2D, kernel, D2H] -> host pinned Tx, every step."""
+    import torch
+    import torch.distributed as dist
+    import psutil
+    n = args.samples
+    n_freqs, n_frames = N_FFT // 2 + 1, (n - 1) // HOP + 1
+    per_ch = n * 4 + n_freqs * n_frames * 8
+    avail = psutil.virtual_memory().available
+    ch = int(min(args.channels, max(1, (0.45 * avail / max(1, world)) // per_ch)))
+    if args.e2e_channels:
+        ch = min(ch, args.e2e_channels)
+    xh = th = None
+    while ch >= 1:
+        try:
+            xh = torch.empty((ch, n), dtype=torch.float32, pin_memory=True)
+            th = torch.empty((ch, n_freqs, n_frames), dtype=torch.complex64, pin_memory=True)
+            break
+        except RuntimeError:
+            xh = th = None
+            ch //= 2
+    if xh is None:
+        return {"value": None, "unit": "Msamples/s", "note": "could not pin host memory"}
+    xh.copy_(x_dev[:ch])
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 3))
+
+    def step():
+        eng.ssq_stft_host(xh.data_ptr(), ch, n, window, N_FFT, HOP, FS, th.data_ptr())
+
+    step()  # warm-up (allocates the device ring)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    val = world * ch * n / (dt / steps) / 1e6
+    chk = float(th[0, :, :64].abs().sum().item())
+    return {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": int(ch * n * 4),
+            "d2h_bytes_per_step": int(ch * n_freqs * n_frames * 8), "channels_per_gpu": ch, "steps": steps,
+            "ms_per_step": dt / steps * 1e3, "checksum": chk,
+            "note": "ssq_ssq_stft_host_f32: pinned host in/out, chunked H2D|kernel|D2H pipeline inside the call"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=CHANNELS)
+    ap.add_argument("--samples", type=int, default=SAMPLES)
+    ap.add_argument("--e2e-channels", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

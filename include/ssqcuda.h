@@ -86,6 +86,8 @@ uint64_t ssq_ctx_launch_count(const ssq_ctx* ctx);
 /* device-time of the most recent batch call's dominant kernel, measured with
  * CUDA events on the context's stream (ms); < 0 when not available */
 float ssq_ctx_last_kernel_ms(ssq_ctx* ctx);
+/* name of that kernel (static string; "" before the first call) */
+const char* ssq_ctx_last_kernel_name(const ssq_ctx* ctx);
 
 /* ---- shape queries ------------------------------------------------------ */
 /* stft.rs:32-34 / ssq_stft.rs:182-184: n_freqs = n_fft/2+1,

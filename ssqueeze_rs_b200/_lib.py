@@ -44,6 +44,7 @@ SIGNATURES = {
     "ssq_ctx_synchronize": (c_int, [c_vp]),
     "ssq_ctx_launch_count": (C.c_uint64, [c_vp]),
     "ssq_ctx_last_kernel_ms": (C.c_float, [c_vp]),
+    "ssq_ctx_last_kernel_name": (C.c_char_p, [c_vp]),
     "ssq_stft_shape": (c_int, [c_i64, c_int, c_int, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "ssq_cwt_shape": (c_int, [c_i64, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "ssq_cwt_default_scales": (c_i64, [c_i64, c_int, c_int, c_vp]),
@@ -138,6 +139,9 @@ class Context:
 
     def last_kernel_ms(self) -> float:
         return float(load().ssq_ctx_last_kernel_ms(self._h))
+
+    def last_kernel_name(self) -> str:
+        return load().ssq_ctx_last_kernel_name(self._h).decode()
 
     def close(self):
         if self._h:

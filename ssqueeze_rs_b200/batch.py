@@ -1,0 +1,157 @@
+"""Multichannel throughput path: replaces the per-channel Python loop around
+`_rs.ssq_stft` (tests/stft_ssq_test.py:230-251 of the reference) by batched
+C-ABI calls on device buffers, and shards channel blocks across the GPUs of one
+box (channels are independent; no collective, host gather only).
+
+`Engine` wraps one device context.  Pointer-level methods take raw device/host
+addresses (what the C ABI takes); tensor-level helpers accept torch CUDA
+tensors (torch is used for device memory and streams only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import PAD, SQUEEZE, Context, load, raise_status
+
+
+def _wptr(window):
+    w = np.ascontiguousarray(window, dtype=np.float64)
+    return w, C.c_void_p(w.ctypes.data)
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.ctx = Context(device)
+        self.device = device
+
+    def last_kernel_name(self) -> str:
+        return self.ctx.last_kernel_name()
+
+    # ---- pointer level ---------------------------------------------------
+    def ssq_stft_ptr(self, d_x, channels, n, window, n_fft, hop, fs, d_Tx, padtype="reflect", squeezing="sum",
+                     gamma=None, modulated=False, x_stride=0):
+        w, wp = _wptr(window)
+        st = load().ssq_ssq_stft_batch_f32(self.ctx.handle, C.c_void_p(d_x), channels, n, x_stride or n, wp, len(w),
+                                           int(n_fft), int(hop), float(fs), PAD.get(padtype, 0),
+                                           SQUEEZE.get(squeezing, 0), -1.0 if gamma is None else float(gamma),
+                                           _lib.FLAG_MODULATED if modulated else 0, C.c_void_p(d_Tx))
+        raise_status(st, self.ctx.handle)
+
+    def stft_ptr(self, d_x, channels, n, window, n_fft, hop, d_Sx, padtype="reflect", x_stride=0):
+        w, wp = _wptr(window)
+        st = load().ssq_stft_batch_f32(self.ctx.handle, C.c_void_p(d_x), channels, n, x_stride or n, wp, len(w),
+                                       int(n_fft), int(hop), PAD.get(padtype, 0), C.c_void_p(d_Sx))
+        raise_status(st, self.ctx.handle)
+
+    def istft_ptr(self, d_Sx, channels, n_freqs, n_frames, window, n_fft, hop, n_out, d_x, win_exp=1):
+        w, wp = _wptr(window)
+        st = load().ssq_istft_batch_f32(self.ctx.handle, C.c_void_p(d_Sx), channels, n_freqs, n_frames, wp, len(w),
+                                        int(n_fft), int(hop), int(n_out), int(win_exp), C.c_void_p(d_x))
+        raise_status(st, self.ctx.handle)
+
+    def issq_stft_ptr(self, d_Tx, channels, n_freqs, n_frames, window, n_fft, fs, d_y):
+        w, wp = _wptr(window)
+        st = load().ssq_issq_stft_batch_f32(self.ctx.handle, C.c_void_p(d_Tx), channels, n_freqs, n_frames, wp,
+                                            len(w), int(n_fft), float(fs), C.c_void_p(d_y))
+        raise_status(st, self.ctx.handle)
+
+    def ssq_stft_host(self, h_x, channels, n, window, n_fft, hop, fs, h_Tx, padtype="reflect", squeezing="sum",
+                      gamma=None, modulated=False):
+        """Host (pinned) buffers in/out; copies inside the call (synchronous)."""
+        w, wp = _wptr(window)
+        st = load().ssq_ssq_stft_host_f32(self.ctx.handle, C.c_void_p(h_x), channels, n, wp, len(w), int(n_fft),
+                                          int(hop), float(fs), PAD.get(padtype, 0), SQUEEZE.get(squeezing, 0),
+                                          -1.0 if gamma is None else float(gamma),
+                                          _lib.FLAG_MODULATED if modulated else 0, C.c_void_p(h_Tx))
+        raise_status(st, self.ctx.handle)
+
+    # ---- tensor level (torch CUDA tensors) ----------------------------------
+    def _bind_stream(self):
+        import torch
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def ssq_stft(self, x, window, n_fft=512, hop_len=32, fs=1.0, out=None, **kw):
+        """x: float32 CUDA tensor [channels, n] -> complex64 [channels, n_freqs, n_frames]."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        ch, n = x.shape
+        nfq, nfr = n_fft // 2 + 1, (n - 1) // hop_len + 1
+        if out is None:
+            out = torch.empty((ch, nfq, nfr), dtype=torch.complex64, device=x.device)
+        self._bind_stream()
+        self.ssq_stft_ptr(x.data_ptr(), ch, n, window, n_fft, hop_len, fs, out.data_ptr(), x_stride=x.stride(0), **kw)
+        return out
+
+    def stft(self, x, window, n_fft, hop_len, out=None, padtype="reflect"):
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        ch, n = x.shape
+        nfq, nfr = n_fft // 2 + 1, (n - 1) // hop_len + 1
+        if out is None:
+            out = torch.empty((ch, nfq, nfr), dtype=torch.complex64, device=x.device)
+        self._bind_stream()
+        self.stft_ptr(x.data_ptr(), ch, n, window, n_fft, hop_len, out.data_ptr(), padtype, x_stride=x.stride(0))
+        return out
+
+    def istft(self, Sx, window, n_fft, hop_len, N=None, win_exp=1):
+        import torch
+        assert Sx.is_cuda and Sx.dtype == torch.complex64 and Sx.dim() == 3 and Sx.is_contiguous()
+        ch, nfq, nfr = Sx.shape
+        n_out = N or hop_len * nfr
+        out = torch.empty((ch, n_out), dtype=torch.float32, device=Sx.device)
+        self._bind_stream()
+        self.istft_ptr(Sx.data_ptr(), ch, nfq, nfr, window, n_fft, hop_len, n_out, out.data_ptr(), win_exp)
+        return out
+
+    def issq_stft(self, Tx, window, n_fft, fs=1.0):
+        import torch
+        assert Tx.is_cuda and Tx.dtype == torch.complex64 and Tx.dim() == 3 and Tx.is_contiguous()
+        ch, nfq, nfr = Tx.shape
+        out = torch.empty((ch, nfr), dtype=torch.float32, device=Tx.device)
+        self._bind_stream()
+        self.issq_stft_ptr(Tx.data_ptr(), ch, nfq, nfr, window, n_fft, fs, out.data_ptr())
+        return out
+
+
+def shard_channels(channels: int, n_devices: int):
+    """Contiguous channel blocks: device g gets [g*C/G, (g+1)*C/G)."""
+    return [(g * channels // n_devices, (g + 1) * channels // n_devices) for g in range(n_devices)]
+
+
+class ChannelSharder:
+    """One host thread + one context per device; numpy host arrays in/out.
+    No inter-GPU traffic: each device works on its own channel block and writes
+    its block of the host result (host gather only)."""
+
+    def __init__(self, devices):
+        self.devices = list(devices)
+        self.engines = [Engine(d) for d in self.devices]
+
+    def ssq_stft(self, x: np.ndarray, window, n_fft=512, hop_len=32, fs=1.0, **kw) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        ch, n = x.shape
+        nfq, nfr = n_fft // 2 + 1, (n - 1) // hop_len + 1
+        out = np.empty((ch, nfq, nfr), dtype=np.complex64)
+        errs = []
+
+        def work(eng, lo, hi):
+            try:
+                if hi > lo:
+                    eng.ssq_stft_host(x[lo:hi].ctypes.data, hi - lo, n, window, n_fft, hop_len, fs,
+                                      out[lo:hi].ctypes.data, **kw)
+            except BaseException as e:  # surfaced below
+                errs.append(e)
+
+        ths = [threading.Thread(target=work, args=(e, lo, hi))
+               for e, (lo, hi) in zip(self.engines, shard_channels(ch, len(self.engines)))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out

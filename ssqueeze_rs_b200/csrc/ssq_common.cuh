@@ -27,6 +27,7 @@ struct ssq_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  const char* last_kernel = "";
   uint64_t launches = 0;
   std::string err;
   // workspaces

@@ -104,6 +104,8 @@ extern "C" float ssq_ctx_last_kernel_ms(ssq_ctx* ctx) {
   return ms;
 }
 
+extern "C" const char* ssq_ctx_last_kernel_name(const ssq_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
+
 extern "C" ssq_status ssq_host_alloc(void** p, size_t bytes) {
   if (!p) return ssq_fail(nullptr, SSQ_EINVAL, "p is NULL");
   cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
@@ -333,6 +335,7 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
                                            (int)tp.smem));
     stft_generic_kernel<<<tp.grid, tp.nw * 32, tp.smem, ctx->stream>>>(P);
     SSQ_TRY(ssq_check_launch(ctx, "stft_generic_kernel"));
+    ctx->last_kernel = "stft_generic_kernel";
   }
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
@@ -449,6 +452,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
                cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
   istft_ola_kernel<<<tp.grid, tp.nw * 32, tp.smem, ctx->stream>>>(P);
   SSQ_TRY(ssq_check_launch(ctx, "istft_ola_kernel"));
+  ctx->last_kernel = "istft_ola_kernel";
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
   dim3 g((unsigned)((n_out + 255) / 256), (unsigned)channels);
@@ -476,6 +480,7 @@ extern "C" ssq_status ssq_issq_stft_batch_f32(ssq_ctx* ctx, const float* d_Tx, i
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   issq_stft_kernel<<<g, 256, 0, ctx->stream>>>((const float2*)d_Tx, n_freqs, n_frames, scale, d_y);
   SSQ_TRY(ssq_check_launch(ctx, "issq_stft_kernel"));
+  ctx->last_kernel = "issq_stft_kernel";
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
   return SSQ_OK;
