@@ -117,6 +117,59 @@ class Engine:
         return out
 
 
+    # ---- CWT family --------------------------------------------------------------
+    def _cwt_args(self, x, scales, fs, t, nv, simd=False):
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        ch, n = x.shape
+        if scales is None:
+            ns = load().ssq_cwt_default_scales(n, int(nv), int(simd), C.c_void_p(0))
+            sc = np.empty(ns, dtype=np.float64)
+            load().ssq_cwt_default_scales(n, int(nv), int(simd), C.c_void_p(sc.ctypes.data))
+        else:
+            sc = np.ascontiguousarray(scales, dtype=np.float64)
+        dt = float(t[1] - t[0]) if t is not None else (1.0 / float(fs) if fs is not None else 1.0)
+        return ch, n, sc, dt
+
+    def cwt(self, x, wavelet="gmw", scales=None, fs=None, t=None, nv=32, l1_norm=True, derivative=False,
+            padtype="reflect", rpadded=False, simd=False):
+        """x: float32 CUDA [channels, n] -> Wx complex64 [channels, ns, n|pad_len] (and dWx)."""
+        import torch
+        ch, n, sc, dt = self._cwt_args(x, scales, fs, t, nv, simd)
+        pl = C.c_int64()
+        load().ssq_cwt_shape(n, C.byref(pl), None)
+        cols = pl.value if rpadded else n
+        Wx = torch.empty((ch, len(sc), cols), dtype=torch.complex64, device=x.device)
+        dWx = torch.empty_like(Wx) if derivative else None
+        flags = (0 if l1_norm else _lib.FLAG_L2_NORM) | (_lib.FLAG_RPADDED if rpadded else 0)
+        self._bind_stream()
+        st = load().ssq_cwt_batch_f32(self.ctx.handle, C.c_void_p(x.data_ptr()), ch, n, x.stride(0),
+                                      1 if wavelet == "morlet" else 0, C.c_void_p(sc.ctypes.data), len(sc), dt,
+                                      PAD.get(padtype, 0), flags, C.c_void_p(Wx.data_ptr()),
+                                      C.c_void_p(dWx.data_ptr() if derivative else 0))
+        raise_status(st, self.ctx.handle)
+        return (Wx, dWx) if derivative else Wx
+
+    def ssq_cwt(self, x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=32, padtype="reflect",
+                squeezing="sum", maprange="peak", gamma=None, flipud=True, out=None, return_freqs=False):
+        """x: float32 CUDA [channels, n] -> Tx complex64 [channels, ns, n]."""
+        import torch
+        ch, n, sc, dt = self._cwt_args(x, scales, fs, t, nv)
+        if out is None:
+            out = torch.empty((ch, len(sc), n), dtype=torch.complex64, device=x.device)
+        sf = np.empty(len(sc), dtype=np.float64)
+        self._bind_stream()
+        st = load().ssq_ssq_cwt_batch_f32(self.ctx.handle, C.c_void_p(x.data_ptr()), ch, n, x.stride(0),
+                                          1 if wavelet == "morlet" else 0, C.c_void_p(sc.ctypes.data), len(sc), dt,
+                                          1 if ssq_freqs == "linear" else 0, PAD.get(padtype, 0),
+                                          SQUEEZE.get(squeezing, 0), 1 if maprange == "maximal" else 0,
+                                          -1.0 if gamma is None else float(gamma),
+                                          0 if flipud else _lib.FLAG_NO_FLIPUD, C.c_void_p(out.data_ptr()),
+                                          C.c_void_p(sf.ctypes.data))
+        raise_status(st, self.ctx.handle)
+        return (out, sf) if return_freqs else out
+
+
 def shard_channels(channels: int, n_devices: int):
     """Contiguous channel blocks: device g gets [g*C/G, (g+1)*C/G)."""
     return [(g * channels // n_devices, (g + 1) * channels // n_devices) for g in range(n_devices)]

@@ -1,18 +1,374 @@
-// cwt_host.inl -- host side of the CWT entry points (included by ssqcuda.cu)
-extern "C" ssq_status ssq_cwt_batch_f32(ssq_ctx* ctx, const float*, int64_t, int64_t, int64_t, int, const double*,
-                                        int64_t, double, int, unsigned, float*, float*) {
-  return ssq_fail(ctx, SSQ_EUNSUPPORTED, "cwt: not built yet");
+// cwt_host.inl -- host side of the CWT entry points (included by ssqcuda.cu).
+
+struct FftPlanHost {
+  int log2L;
+  int npass;
+  int r[8];
+  int log2T;
+};
+
+static FftPlanHost fft_plan(int log2L) {
+  FftPlanHost p;
+  p.log2L = log2L;
+  if (log2L <= 12) {
+    p.npass = 1;
+    p.r[0] = log2L;
+    p.log2T = 0;
+    return p;
+  }
+  p.npass = (log2L + 6) / 7;
+  int left = log2L;
+  for (int i = 0; i < p.npass; ++i) {
+    const int rem = p.npass - i;
+    p.r[i] = (left + rem - 1) / rem;
+    left -= p.r[i];
+  }
+  p.log2T = 5;
+  return p;
 }
-extern "C" ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float*, int64_t, int64_t, int64_t, int,
-                                            const double*, int64_t, double, int, int, int, int, double, unsigned,
-                                            float*, double*) {
-  return ssq_fail(ctx, SSQ_EUNSUPPORTED, "ssq_cwt: not built yet");
+
+static ssq_status cwt_twiddles(ssq_ctx* ctx, int log2L, const float2** lo, const float2** hi, int* tw_s) {
+  const int64_t L = (int64_t)1 << log2L;
+  const int s = (log2L + 1) / 2;
+  const int64_t nlo = (int64_t)1 << s, nhi = (int64_t)1 << (log2L - s);
+  if (ctx->cwt_tw_n != L) {
+    std::vector<float> h((size_t)(nlo + nhi) * 2);
+    for (int64_t i = 0; i < nlo; ++i) {
+      const double a = -2.0 * SSQ_PI * (double)i / (double)L;
+      h[(size_t)2 * i] = (float)std::cos(a);
+      h[(size_t)2 * i + 1] = (float)std::sin(a);
+    }
+    for (int64_t i = 0; i < nhi; ++i) {
+      const double a = -2.0 * SSQ_PI * (double)(i << s) / (double)L;
+      h[(size_t)2 * (nlo + i)] = (float)std::cos(a);
+      h[(size_t)2 * (nlo + i) + 1] = (float)std::sin(a);
+    }
+    SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_tw, h.size() * sizeof(float)));
+    SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_tw.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->cwt_tw_n = L;
+  }
+  *lo = (const float2*)ctx->cwt_tw.p;
+  *hi = *lo + nlo;
+  *tw_s = s;
+  return SSQ_OK;
 }
-extern "C" ssq_status ssq_cwt_f64(ssq_ctx* ctx, const double*, int64_t, int, const double*, int64_t, double, int,
-                                  unsigned, double*, double*) {
-  return ssq_fail(ctx, SSQ_EUNSUPPORTED, "cwt: not built yet");
+
+// Runs all passes of one batched FFT.  `base` carries the functor fields; the
+// first pass uses base.load_mode, the last base.store_mode; in between plain.
+static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int rows, float2* ws0, float2* ws1) {
+  const int64_t L = (int64_t)1 << pl.log2L;
+  int log2Ns = 0;
+  const float2* cur_in = nullptr;
+  for (int i = 0; i < pl.npass; ++i) {
+    FftPass P = base;
+    P.log2L = pl.log2L;
+    P.log2Ns = log2Ns;
+    P.r = pl.r[i];
+    P.log2T = pl.log2T;
+    const bool first = (i == 0), last = (i == pl.npass - 1);
+    if (!first) P.load_mode = 0;
+    if (!last) P.store_mode = 0;
+    P.in = cur_in;
+    float2* o = last ? base.out : ((i & 1) ? ws1 : ws0);
+    P.out = o;
+    const int R = 1 << P.r, T = 1 << P.log2T;
+    const size_t smem = (size_t)2 * R * T * sizeof(float2);
+    dim3 grid((unsigned)(L / ((int64_t)R * T)), (unsigned)rows);
+    SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fft_pass_kernel<<<grid, 256, smem, ctx->stream>>>(P);
+    SSQ_TRY(ssq_check_launch(ctx, "fft_pass_kernel"));
+    cur_in = o;
+    log2Ns += P.r;
+  }
+  return SSQ_OK;
 }
-extern "C" ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double*, int64_t, int, const double*, int64_t, double,
-                                      int, int, int, int, double, unsigned, double*, double*) {
-  return ssq_fail(ctx, SSQ_EUNSUPPORTED, "ssq_cwt: not built yet");
+
+struct CwtCall {
+  const float* d_x;
+  int64_t channels, n, x_stride;
+  int wavelet;
+  const double* scales;
+  int64_t ns;
+  double dt;
+  int padtype;
+  unsigned flags;
+  bool derivative;
+};
+
+// Computes x-hat for `channels` rows into ctx->ws_fft0 region; returns pointers.
+static ssq_status cwt_forward(ssq_ctx* ctx, const CwtCall& c, int log2L, const FftPlanHost& pl, const float2* lo,
+                              const float2* hi, int tw_s, float2* xhat, float2* ws0, float2* ws1) {
+  FftPass B;
+  memset(&B, 0, sizeof(B));
+  B.sign = -1;
+  B.tw_lo = lo;
+  B.tw_hi = hi;
+  B.tw_s = tw_s;
+  B.load_mode = 1;
+  B.x = c.d_x;
+  B.x_stride = c.x_stride;
+  B.n = c.n;
+  B.padtype = c.padtype == SSQ_PAD_ZERO ? SSQ_PAD_ZERO : SSQ_PAD_REFLECT;
+  B.store_mode = 0;
+  const int64_t L = (int64_t)1 << log2L;
+  const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>(32768, ((int64_t)1 << 31) / (L * 8)));
+  for (int64_t r0 = 0; r0 < c.channels; r0 += max_rows) {
+    const int rows = (int)std::min<int64_t>(max_rows, c.channels - r0);
+    B.row0 = r0;
+    B.out = xhat + (size_t)r0 * L;
+    SSQ_TRY(fft_run(ctx, pl, B, rows, ws0, ws1));
+  }
+  return SSQ_OK;
+}
+
+static double cwt_denorm_constant(int wavelet) {
+  return wavelet == SSQ_WAVELET_MORLET ? 1.0 : 2.0 * std::exp(SSQ_GMW_LOGPEAK);
+}
+
+// Shared driver: inverse transforms of rows [g0, g0+rows) in global (channel, scale, which) order.
+static ssq_status cwt_inverse_rows(ssq_ctx* ctx, const CwtCall& c, int log2L, const FftPlanHost& pl,
+                                   const float2* lo, const float2* hi, int tw_s, const float2* xhat,
+                                   const float* d_scales, int nd, float2* outW, float2* outD, int64_t out_cols,
+                                   int64_t n1, float out_scale, int64_t g0, int64_t g1, float2* ws0, float2* ws1,
+                                   int64_t max_rows) {
+  FftPass B;
+  memset(&B, 0, sizeof(B));
+  B.sign = +1;
+  B.tw_lo = lo;
+  B.tw_hi = hi;
+  B.tw_s = tw_s;
+  B.load_mode = 2;
+  B.xhat = xhat;
+  B.scales = d_scales;
+  B.ns = (int)c.ns;
+  B.nd = nd;
+  B.wavelet = c.wavelet == SSQ_WAVELET_MORLET ? SSQ_WAVELET_MORLET : SSQ_WAVELET_GMW;
+  B.inv_dt = (float)(1.0 / c.dt);
+  B.store_mode = 1;
+  B.outW = outW;
+  B.outD = outD;
+  B.out_cols = out_cols;
+  B.n1 = n1;
+  B.out_scale = out_scale;
+  B.l2_norm = (c.flags & SSQ_FLAG_L2_NORM) ? 1 : 0;
+  for (int64_t r0 = g0; r0 < g1; r0 += max_rows) {
+    const int rows = (int)std::min<int64_t>(max_rows, g1 - r0);
+    B.row0 = r0;
+    SSQ_TRY(fft_run(ctx, pl, B, rows, ws0, ws1));
+  }
+  return SSQ_OK;
+}
+
+static ssq_status cwt_prepare(ssq_ctx* ctx, const CwtCall& c, int* log2L, FftPlanHost* pl, const float2** lo,
+                              const float2** hi, int* tw_s, const float** d_scales, float2** xhat, float2** ws0,
+                              float2** ws1, int64_t* max_rows) {
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (c.n < 1 || c.channels < 1) return ssq_fail(ctx, SSQ_EINVAL, "cwt: empty input");
+  if (c.ns < 1) return ssq_fail(ctx, SSQ_EINVAL, "cwt: no scales");
+  if (!(c.dt == c.dt) || c.dt == 0.0) return ssq_fail(ctx, SSQ_EINVAL, "cwt: dt must be non-zero");
+  const int64_t L = ssqhost::next_power_of_2(c.n + c.n / 2);
+  int l2 = 0;
+  while (((int64_t)1 << l2) < L) ++l2;
+  if (l2 > 27) return ssq_fail(ctx, SSQ_EUNSUPPORTED, "cwt: padded length 2^%d too large", l2);
+  *log2L = l2;
+  *pl = fft_plan(l2);
+  SSQ_TRY(cwt_twiddles(ctx, l2, lo, hi, tw_s));
+  // scales -> device fp32
+  std::vector<float> hs((size_t)c.ns);
+  for (int64_t i = 0; i < c.ns; ++i) hs[(size_t)i] = (float)c.scales[i];
+  SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, hs.size() * sizeof(float)));
+  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *d_scales = (const float*)ctx->cwt_scales.p;
+  // workspaces: x-hat [channels, L]; two ping-pong buffers of max_rows rows (multi-pass only)
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft0, (size_t)c.channels * L * sizeof(float2)));
+  *xhat = (float2*)ctx->ws_fft0.p;
+  *max_rows = std::max<int64_t>(1, std::min<int64_t>(32768, ((int64_t)1 << 31) / (L * 8)));
+  *ws0 = *ws1 = nullptr;
+  if (pl->npass > 1) {
+    const int64_t total_rows = std::max<int64_t>(c.channels, c.channels * c.ns * 2);
+    const int64_t mr = std::min<int64_t>(*max_rows, total_rows);
+    *max_rows = mr;
+    const size_t per = (size_t)mr * L * sizeof(float2);
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft1, per * (pl->npass > 2 ? 2 : 1)));
+    *ws0 = (float2*)ctx->ws_fft1.p;
+    *ws1 = pl->npass > 2 ? (float2*)((char*)ctx->ws_fft1.p + per) : nullptr;
+  }
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                        int64_t x_stride, int wavelet, const double* scales, int64_t ns, double dt,
+                                        int padtype, unsigned flags, float* d_Wx, float* d_dWx) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!d_x || !scales || !d_Wx) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  CwtCall c;
+  c.d_x = d_x;
+  c.channels = channels;
+  c.n = n;
+  c.x_stride = x_stride > 0 ? x_stride : n;
+  c.wavelet = wavelet;
+  c.scales = scales;
+  c.ns = ns;
+  c.dt = dt;
+  c.padtype = padtype;
+  c.flags = flags;
+  c.derivative = d_dWx != nullptr;
+  int log2L, tw_s;
+  FftPlanHost pl;
+  const float2 *lo, *hi;
+  const float* d_scales;
+  float2 *xhat, *ws0, *ws1;
+  int64_t max_rows;
+  SSQ_TRY(cwt_prepare(ctx, c, &log2L, &pl, &lo, &hi, &tw_s, &d_scales, &xhat, &ws0, &ws1, &max_rows));
+  const int64_t L = (int64_t)1 << log2L;
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  SSQ_TRY(cwt_forward(ctx, c, log2L, pl, lo, hi, tw_s, xhat, ws0, ws1));
+  const bool rp = (flags & SSQ_FLAG_RPADDED) != 0;
+  const int nd = c.derivative ? 2 : 1;
+  const float out_scale = (float)(cwt_denorm_constant(c.wavelet) / (double)L);
+  SSQ_TRY(cwt_inverse_rows(ctx, c, log2L, pl, lo, hi, tw_s, xhat, d_scales, nd, (float2*)d_Wx, (float2*)d_dWx,
+                           rp ? L : n, rp ? 0 : (L - n) / 2, out_scale, 0, channels * ns * nd, ws0, ws1, max_rows));
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  ctx->last_kernel = "fft_pass_kernel";
+  return SSQ_OK;
+}
+
+// ssq_cwt.rs:447-469 + :135-158: ssq grid and binning constants, in double on the host
+static void ssq_cwt_grid(const double* scales, int64_t ns, int64_t n, double dt, int maprange, int freq_dist,
+                         std::vector<double>& f, int* is_log, double* f0, double* inv_step) {
+  double fmin, fmax;
+  if (maprange == SSQ_MAPRANGE_MAXIMAL) {
+    fmin = 1.0 / ((double)n * dt);
+    fmax = 0.5 / dt;
+  } else {
+    fmin = 1.0 / scales[ns - 1];
+    fmax = 1.0 / scales[0];
+  }
+  f.resize((size_t)ns);
+  if (freq_dist == SSQ_FREQS_LINEAR) {
+    const double step = ns > 1 ? (fmax - fmin) / (double)(ns - 1) : 0.0;
+    for (int64_t i = 0; i < ns; ++i) f[(size_t)i] = fmin + (double)i * step;
+  } else {
+    const double lmin = std::log2(fmin), lmax = std::log2(fmax);
+    const double sf = ns > 1 ? (lmax - lmin) / (double)(ns - 1) : 0.0;
+    for (int64_t i = 0; i < ns; ++i) f[(size_t)i] = std::pow(2.0, lmin + (double)i * sf);
+  }
+  *is_log = (ns > 1) ? (f[1] / f[0] > 1.1) : 0;
+  if (*is_log) {
+    const double lm = std::log2(f[0]);
+    const double ls = ns > 1 ? (std::log2(f[(size_t)ns - 1]) - lm) / (double)(ns - 1) : 1.0;
+    *f0 = lm;
+    *inv_step = 1.0 / ls;
+  } else {
+    const double st = ns > 1 ? (f[(size_t)ns - 1] - f[0]) / (double)(ns - 1) : 1.0;
+    *f0 = f[0];
+    *inv_step = 1.0 / st;
+  }
+}
+
+extern "C" ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                            int64_t x_stride, int wavelet, const double* scales, int64_t ns,
+                                            double dt, int freq_dist, int padtype, int squeezing, int maprange,
+                                            double gamma, unsigned flags, float* d_Tx, double* ssq_freqs) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!d_x || !scales || !d_Tx) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  CwtCall c;
+  c.d_x = d_x;
+  c.channels = channels;
+  c.n = n;
+  c.x_stride = x_stride > 0 ? x_stride : n;
+  c.wavelet = wavelet;
+  c.scales = scales;
+  c.ns = ns;
+  c.dt = dt;
+  c.padtype = padtype;
+  c.flags = 0;  // ssq_cwt is always L1-normalised, unpadded (ssq_cwt.rs:405-435)
+  c.derivative = true;
+  int log2L, tw_s;
+  FftPlanHost pl;
+  const float2 *lo, *hi;
+  const float* d_scales;
+  float2 *xhat, *ws0, *ws1;
+  int64_t max_rows;
+  SSQ_TRY(cwt_prepare(ctx, c, &log2L, &pl, &lo, &hi, &tw_s, &d_scales, &xhat, &ws0, &ws1, &max_rows));
+  const int64_t L = (int64_t)1 << log2L;
+  std::vector<double> f;
+  int is_log;
+  double f0, inv_step;
+  ssq_cwt_grid(scales, ns, n, dt, maprange, freq_dist, f, &is_log, &f0, &inv_step);
+  if (ssq_freqs) memcpy(ssq_freqs, f.data(), sizeof(double) * (size_t)ns);
+  const double K = cwt_denorm_constant(c.wavelet);
+  const double g = (gamma >= 0.0) ? gamma : 10.0 * kEps64;
+  // per-channel W', dW' staging [ns, n] each
+  const size_t stage = (size_t)ns * n * sizeof(float2);
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, stage));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux1, stage));
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  SSQ_TRY(cwt_forward(ctx, c, log2L, pl, lo, hi, tw_s, xhat, ws0, ws1));
+  SSQ_CUDA_TRY(ctx, cudaMemsetAsync(d_Tx, 0, (size_t)channels * stage, ctx->stream));
+  for (int64_t ch = 0; ch < channels; ++ch) {
+    // rows of channel ch; outputs land at row (cs - ch*ns) of the staging buffers
+    float2* W = (float2*)ctx->ws_aux0.p - (size_t)ch * ns * n;
+    float2* D = (float2*)ctx->ws_aux1.p - (size_t)ch * ns * n;
+    SSQ_TRY(cwt_inverse_rows(ctx, c, log2L, pl, lo, hi, tw_s, xhat, d_scales, 2, W, D, n, (L - n) / 2,
+                             (float)(1.0 / (double)L), ch * ns * 2, (ch + 1) * ns * 2, ws0, ws1, max_rows));
+    SsqCwtParams S;
+    memset(&S, 0, sizeof(S));
+    S.W = (const float2*)ctx->ws_aux0.p;
+    S.D = (const float2*)ctx->ws_aux1.p;
+    S.Tx = (float2*)d_Tx + (size_t)ch * ns * n;
+    S.ns = (int)ns;
+    S.n = n;
+    S.gate = (float)(g / K);
+    S.is_log = is_log;
+    S.f0 = (float)f0;
+    S.inv_step = (float)inv_step;
+    S.flipud = (flags & SSQ_FLAG_NO_FLIPUD) ? 0 : 1;
+    S.squeezing = squeezing == SSQ_SQUEEZE_LEBESGUE ? SSQ_SQUEEZE_LEBESGUE : SSQ_SQUEEZE_SUM;
+    S.K = (float)K;
+    S.leb_val = (float)(1.0 / (double)ns);
+    ssq_cwt_reassign_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(S);
+    SSQ_TRY(ssq_check_launch(ctx, "ssq_cwt_reassign_kernel"));
+  }
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  ctx->last_kernel = "fft_pass_kernel+ssq_cwt_reassign_kernel";
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet, const double* scales,
+                                  int64_t ns, double dt, int padtype, unsigned flags, double* Wx, double* dWx) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!x || !scales || !Wx) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n < 1 || ns < 1) return ssq_fail(ctx, SSQ_EINVAL, "cwt: empty input");
+  const int64_t L = ssqhost::next_power_of_2(n + n / 2);
+  const int64_t cols = (flags & SSQ_FLAG_RPADDED) ? L : n;
+  const size_t cnt = (size_t)ns * cols;
+  SSQ_TRY(upload_f64_as_f32(ctx, x, (size_t)n, ctx->ws_in));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, cnt * sizeof(float2)));
+  if (dWx) SSQ_TRY(devbuf_reserve(ctx, ctx->ws_misc, cnt * sizeof(float2)));
+  SSQ_TRY(ssq_cwt_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, n, n, wavelet, scales, ns, dt, padtype, flags,
+                            (float*)ctx->ws_out.p, dWx ? (float*)ctx->ws_misc.p : nullptr));
+  SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_out.p, cnt * 2, Wx));
+  if (dWx) SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_misc.p, cnt * 2, dWx));
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet, const double* scales,
+                                      int64_t ns, double dt, int freq_dist, int padtype, int squeezing, int maprange,
+                                      double gamma, unsigned flags, double* Tx, double* ssq_freqs) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!x || !scales || !Tx) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n < 1 || ns < 1) return ssq_fail(ctx, SSQ_EINVAL, "ssq_cwt: empty input");
+  const size_t cnt = (size_t)ns * n;
+  SSQ_TRY(upload_f64_as_f32(ctx, x, (size_t)n, ctx->ws_in));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, cnt * sizeof(float2)));
+  SSQ_TRY(ssq_ssq_cwt_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, n, n, wavelet, scales, ns, dt, freq_dist,
+                                padtype, squeezing, maprange, gamma, flags, (float*)ctx->ws_out.p, ssq_freqs));
+  return download_f32_as_f64(ctx, ctx->ws_out.p, cnt * 2, Tx);
 }

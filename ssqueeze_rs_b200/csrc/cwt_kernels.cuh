@@ -1,3 +1,242 @@
-// cwt_kernels.cuh -- CWT / ssq_cwt device code (filled in below).
+// cwt_kernels.cuh -- CWT / ssq_cwt device code (sm_100a).
+//
+// Replaces cwt.rs:95-326 / ssq_cwt.rs:331-480: one forward FFT of the padded
+// signal, per-scale multiply by psi-hat (and by i*xi/dt for the derivative),
+// one inverse FFT per (scale, {W, dW}) row, unpad, phase transform and the
+// column-local reassignment.
+//
+// FFT: power-of-two length L = 2^m rows, Stockham autosort in PASSES; a pass
+// applies a radix R = 2^r (r <= 7) to T adjacent columns inside shared memory,
+// so every global access of a pass is a run of T consecutive complex64
+// (256 B for T = 32).  L <= 4096 is a single pass (R = L, T = 1).
+// The first pass LOADS through a functor (real padded signal, or
+// x-hat * psi-hat generated on the fly: the products never exist in HBM); the
+// last pass STORES through a functor (1/L scale, sqrt(scale) for L2 norm,
+// unpad, de-normalisation constant), so Wx is written exactly once.
 #pragma once
 #include "ssq_common.cuh"
+
+struct FftPass {
+  const float2* in;   // [rows, L] (unused by the first pass' functor loads)
+  float2* out;        // [rows, L] (unused by the last pass' functor stores)
+  int log2L, log2Ns, r, log2T;
+  int sign;           // -1 forward, +1 inverse
+  const float2* tw_lo;  // W_L^m, m in [0, 2^tw_s)
+  const float2* tw_hi;  // W_L^(m << tw_s)
+  int tw_s;
+  int64_t row0;       // global row index of row 0 of this launch
+  // ---- load functor -------------------------------------------------------------
+  int load_mode;      // 0 plain, 1 padded real signal, 2 x-hat * psi-hat
+  const float* x;     // [channels, x_stride] (mode 1)
+  int64_t x_stride, n;
+  int padtype;
+  const float2* xhat; // [channels, L] (mode 2)
+  const float* scales;  // [ns] (mode 2)
+  int ns, nd;         // scales per channel, rows per scale (1: W only, 2: W and dW)
+  int wavelet;
+  float inv_dt;
+  // ---- store functor ------------------------------------------------------------
+  int store_mode;     // 0 plain, 1 final: scaled, unpadded rows to outW / outD
+  float2* outW;       // [channels, ns, out_cols]
+  float2* outD;       // [channels, ns, out_cols] (may be NULL)
+  int64_t out_cols, n1;  // out_cols = n (unpadded) or L (rpadded, n1 = 0)
+  float out_scale;    // K / L   (K = de-normalisation constant of psi-hat)
+  int l2_norm;
+};
+
+// GMW(gamma=3, beta=60) is evaluated as exp(60 ln w - w^3 - SSQ_GMW_LOGPEAK): peak 1
+// instead of the reference's un-normalised 2*exp(...) (~4e17, cwt.rs:536-541), which
+// would overflow c*c+d*d in fp32.  The constant is re-applied on store.
+#define SSQ_GMW_WC 2.7144176165949063      /* (60/3)^(1/3) */
+#define SSQ_GMW_LOGPEAK 39.914641217580179 /* 60 ln wc - wc^3 = 20 ln 20 - 20 */
+
+__device__ __forceinline__ float2 tw_lookup(const FftPass& P, int64_t e) {
+  // W_L^e, e in [0, L): two-level table (both tables computed in double on the host)
+  const int lo = (int)(e & ((1 << P.tw_s) - 1));
+  const int hi = (int)(e >> P.tw_s);
+  float2 w = cmulf(__ldg(P.tw_lo + lo), __ldg(P.tw_hi + hi));
+  if (P.sign > 0) w.y = -w.y;
+  return w;
+}
+
+__device__ __forceinline__ float psihat(int wavelet, float w) {
+  if (wavelet == SSQ_WAVELET_MORLET) {
+    // cwt.rs:496-520: pi^-1/4 * sqrt2 * (exp(-(w-6)^2/2) - exp(-18) exp(-w^2/2)), w >= 0
+    if (!(w >= 0.f)) return 0.f;
+    const float norm = 1.0622519320271968f;  // pi^-0.25 * sqrt(2)
+    const float kexp = 1.5229979744712629e-08f;  // exp(-18)
+    const float d = w - 6.f;
+    return norm * (expf(-0.5f * d * d) - kexp * expf(-0.5f * w * w));
+  }
+  // cwt.rs:522-541 (anything else is GMW): 2*exp(60 ln w - w^3), w > 0; normalised here
+  if (!(w > 0.f)) return 0.f;
+  return expf(60.f * logf(w) - w * w * w - (float)SSQ_GMW_LOGPEAK);
+}
+
+__device__ __forceinline__ float cwt_sample(const FftPass& P, int ch, int64_t p, int64_t L) {
+  // utils/array.rs:52-98: left = (L-n)/2
+  const float* x = P.x + (size_t)ch * P.x_stride;
+  const int64_t left = (L - P.n) / 2;
+  const int64_t o = p - left;
+  if (o >= 0 && o < P.n) return __ldg(x + o);
+  if (P.padtype == SSQ_PAD_ZERO) return 0.f;
+  if (o < 0) {
+    const int64_t m = -o;
+    return m < P.n ? __ldg(x + m) : 0.f;
+  }
+  const int64_t m = 2 * P.n - 2 - o;
+  return (m >= 0 && m < P.n) ? __ldg(x + m) : 0.f;
+}
+
+__device__ __forceinline__ float2 pass_load(const FftPass& P, int row, int64_t idx) {
+  const int64_t L = (int64_t)1 << P.log2L;
+  if (P.load_mode == 0) return P.in[(size_t)row * L + idx];
+  const int64_t g = P.row0 + row;
+  if (P.load_mode == 1) return make_float2(cwt_sample(P, (int)g, idx, L), 0.f);
+  // mode 2: row g -> (channel, scale, which)
+  const int which = (int)(g % P.nd);
+  const int64_t cs = g / P.nd;
+  const int si = (int)(cs % P.ns);
+  const int ch = (int)(cs / P.ns);
+  // wavelets/base.rs:18-33 with scale 1: xi = 2 pi idx / L (idx <= L/2), 2 pi (idx - L) / L above
+  const float xi = 6.283185307179586f * ((idx <= (L >> 1)) ? (float)idx : (float)(idx - L)) / (float)L;
+  const float ps = psihat(P.wavelet, __ldg(P.scales + si) * xi);
+  if (ps == 0.f) return make_float2(0.f, 0.f);
+  const float2 xh = __ldg(P.xhat + (size_t)ch * L + idx);
+  float2 v = make_float2(xh.x * ps, xh.y * ps);
+  if (which == 1) {  // * i*xi/dt (cwt.rs:205-209, ssq_cwt.rs:374-377)
+    const float f = xi * P.inv_dt;
+    v = make_float2(-v.y * f, v.x * f);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void pass_store(const FftPass& P, int row, int64_t o, float2 v) {
+  const int64_t L = (int64_t)1 << P.log2L;
+  if (P.store_mode == 0) {
+    P.out[(size_t)row * L + o] = v;
+    return;
+  }
+  const int64_t col = o - P.n1;
+  if (col < 0 || col >= P.out_cols) return;
+  const int64_t g = P.row0 + row;
+  const int which = (int)(g % P.nd);
+  const int64_t cs = g / P.nd;  // channel*ns + scale
+  float s = P.out_scale;
+  if (P.l2_norm) s *= sqrtf(__ldg(P.scales + (int)(cs % P.ns)));  // cwt.rs:253
+  float2* dst = which ? P.outD : P.outW;
+  dst[(size_t)cs * P.out_cols + col] = make_float2(v.x * s, v.y * s);
+}
+
+// grid: (L / (R*T), rows).  Dynamic smem: 2 * R * T float2.
+__global__ void __launch_bounds__(256) fft_pass_kernel(const FftPass P) {
+  extern __shared__ float2 smem[];
+  const int R = 1 << P.r, T = 1 << P.log2T;
+  const int64_t L = (int64_t)1 << P.log2L;
+  const int64_t Ns = (int64_t)1 << P.log2Ns;
+  const int64_t Q = L >> P.r;  // L / R: number of butterflies per row
+  float2* A = smem;
+  float2* B = smem + R * T;
+  const int row = blockIdx.y;
+  const int64_t j0 = (int64_t)blockIdx.x * T;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int twshift = P.log2L - P.log2Ns - P.r;  // W_{Ns R}^e = W_L^(e << twshift)
+
+  for (int e = tid; e < R * T; e += nt) {
+    const int t = e >> P.log2T, c = e & (T - 1);
+    const int64_t j = j0 + c;
+    float2 v = pass_load(P, row, j + (int64_t)t * Q);
+    if (P.log2Ns > 0 && t > 0) {
+      const int64_t k = j & (Ns - 1);
+      v = cmulf(v, tw_lookup(P, (k * t) << twshift));
+    }
+    A[e] = v;
+  }
+  __syncthreads();
+  // R-point DFT along t for each of the T columns: radix-2 Stockham sub-stages
+  const int half = (R >> 1) * T;
+  for (int s = 0; s < P.r; ++s) {
+    const int ns = 1 << s;
+    const int sub_shift = P.log2L - (s + 1);  // W_{2 ns}^kk = W_L^(kk << sub_shift)
+    for (int e = tid; e < half; e += nt) {
+      const int b = e >> P.log2T, c = e & (T - 1);
+      const int kk = b & (ns - 1);
+      const float2 a = A[b * T + c];
+      float2 bb = A[(b + (R >> 1)) * T + c];
+      if (kk) bb = cmulf(bb, tw_lookup(P, (int64_t)kk << sub_shift));
+      const int o = ((b - kk) << 1) + kk;
+      B[o * T + c] = caddf(a, bb);
+      B[(o + ns) * T + c] = csubf(a, bb);
+    }
+    __syncthreads();
+    float2* t2 = A; A = B; B = t2;
+  }
+  // store: out[(j-k)*R + k + t*Ns], k = j mod Ns
+  if (Ns >= T) {
+    for (int e = tid; e < R * T; e += nt) {
+      const int t = e >> P.log2T, c = e & (T - 1);
+      const int64_t j = j0 + c;
+      const int64_t k = j & (Ns - 1);
+      pass_store(P, row, ((j - k) << P.r) + k + (int64_t)t * Ns, A[e]);
+    }
+  } else {
+    // Ns < T: the CTA's outputs form one contiguous block [j0*R, (j0+T)*R)
+    const int nsr = (int)(Ns << P.r);
+    for (int e = tid; e < R * T; e += nt) {
+      const int a = e / nsr, rem = e - a * nsr;
+      const int t = rem >> P.log2Ns, k = rem & ((int)Ns - 1);
+      const int c = a * (int)Ns + k;
+      pass_store(P, row, (j0 << P.r) + e, A[t * T + c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// ssq_cwt reassignment (ssq_cwt.rs:116-222 + phase_cwt :15-47): one thread per time
+// column; the thread is the only writer of its Tx column, so the accumulation is
+// a plain read-modify-write in ascending scale order (the reference's order).
+// W, D: [ns, n] (already scaled by 1/L, psi-hat peak-normalised: true Wx = W * K).
+// ------------------------------------------------------------------------------------
+struct SsqCwtParams {
+  const float2* W;
+  const float2* D;
+  float2* Tx;         // [ns, n] zero-initialised
+  int ns;
+  int64_t n;
+  float gate;         // gamma / K : |W| < gate -> skipped
+  int is_log;
+  float f0, inv_step; // lin: (w - f0) * inv_step ; log: (log2 w - f0) * inv_step
+  int flipud, squeezing;
+  float K, leb_val;
+};
+
+__global__ void ssq_cwt_reassign_kernel(const SsqCwtParams P) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.n) return;
+  for (int i = 0; i < P.ns; ++i) {
+    float2 Wv = P.W[(size_t)i * P.n + b];
+    float2 Dv = P.D[(size_t)i * P.n + b];
+    const float mag = hypotf(Wv.x, Wv.y);
+    if (mag < P.gate) continue;  // ssq_cwt.rs:29-30
+    float c = Wv.x, d = Wv.y, a = Dv.x, bb = Dv.y;
+    if (mag < 1e-15f) {  // keep c*c+d*d away from fp32 underflow; the ratio is scale-free
+      const float up = 1.8446744e19f;  // 2^64
+      c *= up; d *= up; a *= up; bb *= up;
+    } else if (mag > 1e15f) {
+      const float dn = 5.4210109e-20f;  // 2^-64
+      c *= dn; d *= dn; a *= dn; bb *= dn;
+    }
+    const float w = fabsf((bb * c - a * d) / ((c * c + d * d) * 6.283185307179586f));
+    if (!(w <= 3.4028235e38f)) continue;  // inf / NaN skipped (:167-169)
+    const float v = P.is_log ? (log2f(w) - P.f0) * P.inv_step : (w - P.f0) * P.inv_step;
+    const float r = roundf(v);  // f64::round: half away from zero (:176, :187)
+    if (!(r >= 0.f && r < (float)P.ns)) continue;  // out of range dropped (:177-179)
+    const int bin = (int)r;
+    const int k = P.flipud ? P.ns - 1 - bin : bin;
+    float2* t = P.Tx + (size_t)k * P.n + b;
+    float2 cur = *t;
+    if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) cur.x += P.leb_val;
+    else { cur.x += Wv.x * P.K; cur.y += Wv.y * P.K; }
+    *t = cur;
+  }
+}

@@ -25,7 +25,7 @@
 #define SSQ_FAST_N 512
 #define SSQ_FAST_F 32            // frames per tile
 #define SSQ_FAST_WARPS 8
-#define SSQ_FAST_ACC_STRIDE 257  // odd -> conflict-free transposed read-out
+#define SSQ_FAST_ACC_STRIDE 289  // bin k lives at k + (k>>3) (max 288); odd stride -> conflict-free read-out
 #define SSQ_FAST_MAX_HOP 64
 
 __device__ __forceinline__ void fft8_fwd(float2 (&v)[8]) {
@@ -54,24 +54,68 @@ __device__ __forceinline__ void fft8_fwd(float2 (&v)[8]) {
   v[7] = make_float2(fmaf(-S, r7.x, b6.x), fmaf(-S, r7.y, b6.y));
 }
 
-// One bin of the epilogue: zk = Z[k], zn = Z[N-k].
+// Bin k of a frame's accumulator column lives at k + (k >> 3): one pad slot per 8
+// bins, so that lanes owning bins 8 apart (the reassignment phase) and lanes owning
+// consecutive bins (the stft store) both hit distinct banks.
+__device__ __forceinline__ int acc_phys(int k) { return k + (k >> 3); }
+
+// One bin of the epilogue: zk = Z[k], zn = Z[N-k].  MODE 1 stores Sx; MODE 0 parks
+// the item (value to add, destination bin or -1 when gated) in the per-warp staging
+// area, indexed by the SOURCE bin k.
 template <int MODE>
-__device__ __forceinline__ void ssq_epilogue_bin(const StftParams& P, float2* col, int k, float2 zk, float2 zn) {
+__device__ __forceinline__ void ssq_epilogue_bin(const StftParams& P, float2* col, float2* sval, int* skey, int k,
+                                                 float2 zk, float2 zn) {
   const float c = zk.x + zn.x, d = zk.y - zn.y;  // 2*Sx
   if (MODE == 1) {
-    col[k] = make_float2(0.5f * c, 0.5f * d);
+    col[acc_phys(k)] = make_float2(0.5f * c, 0.5f * d);
     return;
   }
   const float a = zk.y + zn.y, b = zn.x - zk.x;  // 2*V
   const float den = fmaf(c, c, d * d);
   const float num = fmaf(b, c, -a * d);
-  if (den < P.gate2) return;                      // |Sx| < gamma (ssq_stft.rs:23)
   const float q = __fdividef(num, den) * P.cphase;
   const float binf = fabsf((float)k - q);
   const float r = ceilf(binf - 0.5f);
-  const int kb = (int)fminf(fmaxf(r, 0.f), 256.f);  // fmaxf(NaN, 0) = 0 -> bin 0 like the reference
-  if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) smem_add_f2(&col[kb], P.leb_val, 0.f);
-  else smem_add_f2(&col[kb], c * P.tx_scale, d * P.tx_scale);
+  int kb = (int)fminf(fmaxf(r, 0.f), 256.f);  // fmaxf(NaN, 0) = 0 -> bin 0 like the reference
+  if (den < P.gate2) kb = -1;                  // |Sx| < gamma (ssq_stft.rs:23): dropped
+  float2 v = make_float2(c * P.tx_scale, d * P.tx_scale);
+  if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) v = make_float2(P.leb_val, 0.f);
+  sval[acc_phys(k)] = v;
+  skey[k] = kb;
+}
+
+// Adds the lane's item (bin kb or -1) into the frame column.  All 32 lanes call it
+// together.  fp32 shared atomics are CAS loops on sm_100a and cost ~2 cycles per
+// lane, so none are used: a byte tag per bin detects the (rare) case of two lanes
+// aiming at the same bin in the same step; otherwise every lane does a plain
+// read-modify-write.  Lanes own 8 CONSECUTIVE source bins each and walk them in
+// ascending order, which is the reference's accumulation order (ssq_stft.rs:277).
+__device__ __forceinline__ void ssq_accumulate_step(float2* col, unsigned char* tag, int kb, float2 v, int lane) {
+  const bool on = kb >= 0;
+  if (on) tag[kb] = (unsigned char)lane;
+  __syncwarp();
+  const bool mine = !on || tag[on ? kb : 0] == (unsigned char)lane;
+  if (__all_sync(0xffffffffu, mine)) {
+    if (on) {
+      float2* p = col + acc_phys(kb);
+      float2 t = *p;
+      t.x += v.x;
+      t.y += v.y;
+      *p = t;
+    }
+  } else {
+    for (int src = 0; src < 32; ++src) {  // collision: serialise the lanes (ascending source order)
+      if (lane == src && on) {
+        float2* p = col + acc_phys(kb);
+        float2 t = *p;
+        t.x += v.x;
+        t.y += v.y;
+        *p = t;
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
 }
 
 template <int MODE>
@@ -189,8 +233,11 @@ __global__ void __launch_bounds__(SSQ_FAST_WARPS * 32, 2) ssq_stft512_kernel(con
       }
       fft8_fwd(va);  // va[m] = X[lane + 64 m]
       fft8_fwd(vb);  // vb[m] = X[j2 + 64 m]
-      // ---- split + phase + reassignment ------------------------------------------------
+      // ---- split + phase transform (lanes own strided bins here) -----------------------
       float2* col = acc + fl * AS;
+      float2* sval = xch;                                        // [289] items by source bin
+      int* skey = reinterpret_cast<int*>(xch + 296);             // [257]
+      unsigned char* tag = reinterpret_cast<unsigned char*>(xch + 432);  // [257]
       const bool l0 = (lane == 0);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
@@ -198,7 +245,7 @@ __global__ void __launch_bounds__(SSQ_FAST_WARPS * 32, 2) ssq_stft512_kernel(con
         float2 pa = vb[7 - m];
         const float2 alt = va[(8 - m) & 7];
         if (l0) pa = alt;
-        ssq_epilogue_bin<MODE>(P, col, lane + 64 * m, va[m], pa);
+        ssq_epilogue_bin<MODE>(P, col, sval, skey, lane + 64 * m, va[m], pa);
       }
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
@@ -206,22 +253,42 @@ __global__ void __launch_bounds__(SSQ_FAST_WARPS * 32, 2) ssq_stft512_kernel(con
         float2 pb = va[7 - m];
         const float2 alt = vb[7 - m];
         if (l0) pb = alt;
-        ssq_epilogue_bin<MODE>(P, col, j2 + 64 * m, vb[m], pb);
+        ssq_epilogue_bin<MODE>(P, col, sval, skey, j2 + 64 * m, vb[m], pb);
       }
-      if (l0) ssq_epilogue_bin<MODE>(P, col, 256, va[4], va[4]);
+      if (l0) ssq_epilogue_bin<MODE>(P, col, sval, skey, 256, va[4], va[4]);
+      if (MODE == 0) {
+        __syncwarp();
+        // ---- reassignment: lane owns source bins 8*lane .. 8*lane+7 (lane 31 also 256) ----
+        const int4 k0 = *reinterpret_cast<const int4*>(skey + 8 * lane);
+        const int4 k1 = *reinterpret_cast<const int4*>(skey + 8 * lane + 4);
+        float2 it[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) it[j] = sval[9 * lane + j];
+        const int k8 = (lane == 31) ? skey[256] : -1;
+        const float2 it8 = sval[288];
+        __syncwarp();
+        ssq_accumulate_step(col, tag, k0.x, it[0], lane);
+        ssq_accumulate_step(col, tag, k0.y, it[1], lane);
+        ssq_accumulate_step(col, tag, k0.z, it[2], lane);
+        ssq_accumulate_step(col, tag, k0.w, it[3], lane);
+        ssq_accumulate_step(col, tag, k1.x, it[4], lane);
+        ssq_accumulate_step(col, tag, k1.y, it[5], lane);
+        ssq_accumulate_step(col, tag, k1.z, it[6], lane);
+        ssq_accumulate_step(col, tag, k1.w, it[7], lane);
+        ssq_accumulate_step(col, tag, k8, it8, lane);
+      }
+      __syncwarp();  // the staging area is the exchange buffer of the next frame
     }
     __syncthreads();
     // ---- coalesced store of the tile (and re-zero of the accumulator) -------------------
     {
       float2* outc = P.out + (size_t)ch * P.n_freqs * P.n_frames + f0;
-      if (lane < nf) {
-        for (int k = warp; k < 257; k += SSQ_FAST_WARPS) {
-          const float2 v = acc[lane * AS + k];
-          outc[(size_t)k * P.n_frames + lane] = v;
-        }
+      // each warp re-zeroes exactly the slots it has just read (the pad slots 9m+8 are never touched)
+      for (int k = warp; k < 257; k += SSQ_FAST_WARPS) {
+        float2* a = acc + lane * AS + acc_phys(k);
+        if (lane < nf) outc[(size_t)k * P.n_frames + lane] = *a;
+        if (MODE == 0) *a = make_float2(0.f, 0.f);
       }
-      if (MODE == 0)
-        for (int k = warp; k < 257; k += SSQ_FAST_WARPS) acc[lane * AS + k] = make_float2(0.f, 0.f);
     }
     __syncthreads();
   }

@@ -1,0 +1,168 @@
+"""GPU parity of the CWT path (`cwt`, `cwt_simd`, `ssq_cwt`) against the float64
+oracle (cwt.rs / cwt_simd.rs / ssq_cwt.rs restatement).  Tolerance: rtol 1e-4 of
+the array maximum (fp32 arithmetic); reassignment flips at bin edges are counted
+and bounded."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ssq_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-4
+
+
+def _rs():
+    from ssqueeze_rs_b200 import _rs
+    return _rs
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def sine():
+    fs = 1000
+    t = np.linspace(0, 1, fs, endpoint=False)
+    return np.sin(2 * np.pi * 100 * t), fs
+
+
+def test_cwt_readme_shapes_and_values():
+    """tests/cwt_test.py:19-57 and tests/cwt_simd_test.py:19-57 re-hosted."""
+    rs = _rs()
+    x, fs = sine()
+    scales = np.logspace(1, 5, 32) / fs
+    z = np.load(os.path.join(G, "readme_cases.npz"))
+    for fn in (rs.cwt, rs.cwt_simd):
+        out = fn(x, wavelet="gmw", scales=scales, fs=fs, nv=16, derivative=True)
+        assert len(out) == 3  # always a 3-tuple (cwt.rs:60,143)
+        Wx, sc, dWx = out
+        assert Wx.shape == (32, 1000) and dWx.shape == (32, 1000) and Wx.dtype == np.complex128
+        assert np.array_equal(sc, scales)
+        Wo, _, dWo = O.cwt(x, "gmw", scales, fs=float(fs), nv=16, derivative=True)
+        assert rel(Wx, Wo) < RTOL and rel(dWx, dWo) < RTOL
+        rows = z["cwt_gmw_rows"]
+        assert rel(Wx[rows], z["cwt_gmw_Wx_rows"]) < RTOL
+    Wx, sc, dWx = rs.cwt(x, "morlet", scales, fs=fs)
+    assert dWx is None
+    Wo, _, _ = O.cwt(x, "morlet", scales, fs=float(fs))
+    assert rel(Wx, Wo) < RTOL
+    assert rel(Wx[z["cwt_morlet_rows"]], z["cwt_morlet_Wx_rows"]) < RTOL
+
+
+@pytest.mark.parametrize("wavelet", ["gmw", "morlet", "unknown-falls-back-to-gmw"])
+@pytest.mark.parametrize("N", [777, 1000, 3000, 20000])
+def test_cwt_noise_default_scales(wavelet, N):
+    rs = _rs()
+    x = np.random.default_rng(N).standard_normal(N)
+    nv = 8 if N < 5000 else 2
+    Wx, sc, dWx = rs.cwt(x, wavelet, None, fs=250.0, nv=nv, derivative=True)
+    Wo, so, dWo = O.cwt(x, wavelet, None, fs=250.0, nv=nv, derivative=True)
+    assert np.allclose(sc, so, rtol=1e-14)
+    assert Wx.shape == Wo.shape
+    assert rel(Wx, Wo) < RTOL, rel(Wx, Wo)
+    assert rel(dWx, dWo) < RTOL, rel(dWx, dWo)
+    # cwt_simd: exp(p ln2) scale generator (cwt_simd.rs:489-527)
+    W2, s2, _ = rs.cwt_simd(x, wavelet, None, fs=250.0, nv=nv)
+    assert np.allclose(s2, O.generate_log_scales(N, nv, simd=True), rtol=1e-14)
+    assert rel(W2, Wo) < RTOL
+
+
+def test_cwt_options():
+    rs = _rs()
+    x = np.random.default_rng(1).standard_normal(1500)
+    sc = np.array([2.0, 3.5, 8.0, 20.0, 77.0])
+    for kw in (dict(l1_norm=False), dict(padtype="zero"), dict(rpadded=True), dict(t=np.arange(1500) * 0.004),
+               dict(vectorized=False), dict(padtype="nonsense"), dict(rpadded=True, l1_norm=False, derivative=True)):
+        Wx, s, dWx = rs.cwt(x, "gmw", sc, **kw)
+        Wo, so, dWo = O.cwt(x, "gmw", sc, **kw)
+        assert Wx.shape == Wo.shape, kw
+        assert rel(Wx, Wo) < RTOL, kw
+        if dWo is not None:
+            assert rel(dWx, dWo) < RTOL, kw
+    with pytest.raises(ValueError):
+        rs.cwt(x, t=np.array([0.0]))
+    with pytest.raises(TypeError):
+        rs.cwt(x.astype(np.float32))
+
+
+def _ssq_compare(Tx, To, max_bad=5e-3):
+    sc = np.abs(To).max()
+    bad = np.abs(Tx - To) > RTOL * sc
+    assert bad.mean() < max_bad, bad.mean()
+    e_g, e_o = np.abs(Tx).sum(), np.abs(To).sum()
+    assert abs(e_g - e_o) < 2e-3 * e_o
+    return float(bad.mean())
+
+
+def test_ssq_cwt_readme_cases():
+    """tests/ssq_cwt_test.py:19-57 (explicit scales, peak) and :410-419 (defaults, maximal)."""
+    rs = _rs()
+    x, fs = sine()
+    scales = np.logspace(1, 5, 32) / fs
+    z = np.load(os.path.join(G, "readme_cases.npz"))
+    for wav in ("gmw", "morlet"):
+        Tx, sf = rs.ssq_cwt(x, wavelet=wav, scales=scales, fs=fs, nv=16, padtype="reflect", squeezing="sum",
+                            maprange="peak")
+        assert Tx.shape == (32, 1000) and sf.shape == (32,)
+        To, sfo = O.ssq_cwt(x, wav, scales, fs=float(fs), nv=16)
+        assert np.allclose(sf, sfo, rtol=1e-13) and np.allclose(sf, z[f"ssq_cwt_{wav}_freqs"], rtol=1e-13)
+        _ssq_compare(Tx, To)
+    Tx, sf = rs.ssq_cwt(x, wavelet="gmw", scales=None, fs=fs, nv=32, squeezing="sum", maprange="maximal", gamma=1e-6)
+    To, sfo = O.ssq_cwt(x, "gmw", None, fs=float(fs), nv=32, maprange="maximal", gamma=1e-6)
+    assert Tx.shape == To.shape and np.allclose(sf, sfo, rtol=1e-13)
+    _ssq_compare(Tx, To)
+    assert np.allclose(np.abs(Tx).sum(axis=1), z["ssq_cwt_maximal_Tx_abs_rowsum"], rtol=5e-3,
+                       atol=2e-3 * z["ssq_cwt_maximal_Tx_abs_rowsum"].max())
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(maprange="maximal"), dict(ssq_freqs="linear", maprange="maximal"),
+                                dict(squeezing="lebesgue", maprange="maximal"), dict(flipud=False, maprange="maximal"),
+                                dict(padtype="zero", maprange="maximal"), dict(gamma=0.5, maprange="maximal"),
+                                dict(wavelet="morlet", maprange="maximal")])
+def test_ssq_cwt_chirp_noise(kw):
+    rs = _rs()
+    N = 4096
+    t = np.arange(N) / 1000.0
+    rng = np.random.default_rng(3)
+    x = np.sin(2 * np.pi * (20 * t + 0.5 * 40 * t ** 2)) + 0.5 * rng.standard_normal(N)
+    kw = dict(kw)
+    wav = kw.pop("wavelet", "gmw")
+    Tx, sf = rs.ssq_cwt(x, wav, None, fs=1000.0, nv=8, **kw)
+    To, sfo = O.ssq_cwt(x, wav, None, fs=1000.0, nv=8, **kw)
+    assert Tx.shape == To.shape and np.allclose(sf, sfo, rtol=1e-13)
+    if kw.get("squeezing") == "lebesgue":
+        bad = np.abs(Tx - To) > 1e-6
+        assert bad.mean() < 5e-3
+    else:
+        _ssq_compare(Tx, To)
+
+
+def test_ssq_cwt_multipass_fft_and_batch():
+    """pad_len 2^15 (three FFT passes) and the batched device entry point."""
+    import torch
+    from ssqueeze_rs_b200 import _lib
+    from ssqueeze_rs_b200.batch import Engine
+    rs = _rs()
+    N = 20000
+    t = np.arange(N) / 1000.0
+    rng = np.random.default_rng(4)
+    x = np.sin(2 * np.pi * (5 * t + 0.5 * 20 * t ** 2)) + 0.5 * rng.standard_normal(N)
+    sc = 2.0 ** np.linspace(1, 9, 24)
+    Tx, sf = rs.ssq_cwt(x, "gmw", sc, fs=1000.0, maprange="maximal")
+    To, sfo = O.ssq_cwt(x, "gmw", sc, fs=1000.0, maprange="maximal")
+    _ssq_compare(Tx, To)
+    eng = Engine(0)
+    xb = np.stack([x, x[::-1].copy(), 2 * x]).astype(np.float32)
+    out = eng.ssq_cwt(torch.from_numpy(xb).cuda(), "gmw", sc, fs=1000.0, maprange="maximal")
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    assert out.shape == (3, 24, N)
+    _ssq_compare(out[0].astype(np.complex128), To)
+    assert np.allclose(out[2], 2 * out[0], rtol=1e-5, atol=1e-5 * np.abs(out[0]).max())
+    W = eng.cwt(torch.from_numpy(xb).cuda(), "gmw", sc, fs=1000.0)
+    torch.cuda.synchronize()
+    Wo, _, _ = O.cwt(xb[1].astype(np.float64), "gmw", sc, fs=1000.0)
+    assert rel(W[1].cpu().numpy(), Wo) < RTOL

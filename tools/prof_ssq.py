@@ -1,0 +1,48 @@
+"""Small driver for ncu / quick timing: runs the batched ssq_stft (or another
+op) a few times on synthetic noise.  Not part of the product or the tests."""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from ssqueeze_rs_b200.batch import Engine  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--channels", type=int, default=32)
+ap.add_argument("--samples", type=int, default=1_800_000)
+ap.add_argument("--n-fft", type=int, default=512)
+ap.add_argument("--hop", type=int, default=32)
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--op", default="ssq_stft")
+ap.add_argument("--signal", default="noise", choices=["noise", "tone", "neural"])
+a = ap.parse_args()
+
+eng = Engine(0)
+g = torch.Generator(device="cuda")
+g.manual_seed(0)
+if a.signal == "noise":
+    x = torch.randn((a.channels, a.samples), generator=g, device="cuda") * 10
+elif a.signal == "tone":
+    t = torch.arange(a.samples, device="cuda", dtype=torch.float64) / 30000.0
+    x = torch.sin(2 * np.pi * 1000.0 * t).to(torch.float32).repeat(a.channels, 1).contiguous()
+else:
+    from bench import make_neural
+    x = make_neural(torch, a.channels, a.samples, 30000.0, torch.device("cuda", 0), 1)
+win = np.hanning(a.n_fft)
+nfq, nfr = a.n_fft // 2 + 1, (a.samples - 1) // a.hop + 1
+out = torch.empty((a.channels, nfq, nfr), dtype=torch.complex64, device="cuda")
+torch.cuda.synchronize()
+for it in range(a.iters):
+    if a.op == "ssq_stft":
+        eng.ssq_stft(x, win, a.n_fft, a.hop, 30000.0, out=out)
+    elif a.op == "stft":
+        eng.stft(x, win, a.n_fft, a.hop, out=out)
+    ms = eng.ctx.last_kernel_ms()
+    ab = a.channels * (4 * a.samples + 8 * nfq * nfr)
+    print(f"{eng.last_kernel_name()} iter {it}: {ms:.3f} ms  {a.channels * a.samples / ms / 1e3:.1f} Msamples/s  "
+          f"{ab / ms / 1e6:.1f} GB/s algorithmic")
+torch.cuda.synchronize()
