@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -78,9 +78,14 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -91,7 +96,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = [ln for (t, ln) in self.lines if t_begin is None or (t_begin <= t <= t_end + 0.06)]
+        if not lines:  # region shorter than one sampling period: nearest samples around it
+            lines = [ln for (t, ln) in self.lines if t_begin - 0.3 <= t <= t_end + 0.3]
+        for ln in lines:
             f = [s.strip() for s in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -168,6 +176,7 @@ def make_neural_cpu(channels, n, fs, seed):
 def cpu_reference_run(n_samples, steps, warmup, mode=0, channels=1):
     """Times the C restatement (oracle/ssq_stft_ref.c) on `channels` x n_samples."""
     from oracle import cref
+    cref.use_all_cores()
     x = make_neural_cpu(channels, n_samples, FS, 0x5351)
     w = np.hanning(N_FFT)
     times = []
@@ -183,7 +192,7 @@ def cpu_reference_run(n_samples, steps, warmup, mode=0, channels=1):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n_s = 450_000
+    n_s = args.ref_samples
     steps = max(1, min(args.steps, 20))
     warm = max(1, min(args.warmup, 3))
     msps, threads, sec = cpu_reference_run(n_s, steps, warm, mode=0)
@@ -220,40 +229,45 @@ def run_ours(args, rank, world, local_rank):
     x = make_neural(torch, channels, n, FS, dev, 0x5351 + rank)
     Tx = torch.empty((channels, n_freqs, n_frames), dtype=torch.complex64, device=dev)
     torch.cuda.synchronize()
-    eng.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=dev)  # the kernels, the step events and the timed region share this stream
+    eng.ctx.set_stream(stream.cuda_stream)
 
     def step():
         eng.ssq_stft_ptr(x.data_ptr(), channels, n, window, N_FFT, HOP, FS, Tx.data_ptr())
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = eng.ctx.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-        kernel_ms.append(eng.ctx.last_kernel_ms())
-    ev1.record()
+    sampler.wait_first()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
-    launches = eng.ctx.launch_count() - launches0
-    total_ms = ev0.elapsed_time(ev1)
-    tms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    t_begin = time.time()
+    launches0 = eng.ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for a, b in kev:
+            a.record(stream)
+            step()
+            b.record(stream)
+        ev1.record(stream)
+    torch.cuda.synchronize()
     if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    total_ms = float(tms.item())
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_end = time.time()
+    kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    clocks = sampler.stop(t_begin, t_end)
+    launches = eng.ctx.launch_count() - launches0
+    from ssqueeze_rs_b200.dist import job_throughput
+    per_s, total_ms = job_throughput(float(channels) * n * args.steps, ev0.elapsed_time(ev1), dev)
     ms_per_step = total_ms / args.steps
-    value = world * channels * n / (ms_per_step * 1e-3) / 1e6
+    value = per_s / 1e6
 
     # checksum so the timed work cannot be optimised away / silently skipped
     chk = float(torch.view_as_real(Tx[0, :, :64]).abs().sum().item())
@@ -359,6 +373,7 @@ def main():
     ap.add_argument("--samples", type=int, default=SAMPLES)
     ap.add_argument("--e2e-channels", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-samples", type=int, default=450_000, help="samples per step of the reference arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -21,11 +21,19 @@ def load():
         _lib.ssq_stft_ref.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int,
                                       C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.ssq_ref_num_threads.restype = C.c_int
+        _lib.ssq_ref_set_threads.argtypes = [C.c_int]
     return _lib
 
 
 def num_threads():
     return load().ssq_ref_num_threads()
+
+
+def use_all_cores():
+    """The Rayon global pool uses every host core; do the same (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().ssq_ref_set_threads(n)
+    return num_threads()
 
 
 def ssq_stft(x, window_fit, n_fft, hop, fs, padtype="reflect", squeezing="sum", gamma=None, mode=0,

@@ -256,6 +256,11 @@ int ssq_stft_ref(const double* x, int64_t n, const double* window, int n_fft, in
   return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants all host cores */
+void ssq_ref_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+
 int ssq_ref_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -72,7 +72,10 @@ class Engine:
     # ---- tensor level (torch CUDA tensors) ----------------------------------
     def _bind_stream(self):
         import torch
-        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        h = torch.cuda.current_stream(self.device).cuda_stream
+        # handle 0 is the legacy default stream; the C ABI reserves NULL for "the context's own
+        # stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1)
+        self.ctx.set_stream(h if h else 1)
 
     def ssq_stft(self, x, window, n_fft=512, hop_len=32, fs=1.0, out=None, **kw):
         """x: float32 CUDA tensor [channels, n] -> complex64 [channels, n_freqs, n_frames]."""

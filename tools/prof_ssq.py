@@ -19,6 +19,7 @@ ap.add_argument("--hop", type=int, default=32)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--op", default="ssq_stft")
 ap.add_argument("--signal", default="noise", choices=["noise", "tone", "neural"])
+ap.add_argument("--nv", type=int, default=32)
 a = ap.parse_args()
 
 eng = Engine(0)
@@ -34,6 +35,41 @@ else:
     x = make_neural(torch, a.channels, a.samples, 30000.0, torch.device("cuda", 0), 1)
 win = np.hanning(a.n_fft)
 nfq, nfr = a.n_fft // 2 + 1, (a.samples - 1) // a.hop + 1
+if a.op in ("ssq_cwt", "cwt"):
+    import ctypes as C
+    from ssqueeze_rs_b200._lib import load
+    ns = load().ssq_cwt_default_scales(a.samples, a.nv, 0, C.c_void_p(0))
+    out = torch.empty((a.channels, ns, a.samples), dtype=torch.complex64, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(a.iters):
+        ev0.record()
+        if a.op == "ssq_cwt":
+            eng.ssq_cwt(x, "gmw", None, fs=30000.0, nv=a.nv, maprange="maximal", out=out)
+        else:
+            out = eng.cwt(x, "gmw", None, fs=30000.0, nv=a.nv)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)  # Engine binds the legacy default stream: the events bracket the kernels
+        ab = a.channels * (4 * a.samples + 8 * ns * a.samples)
+        print(f"{a.op} ns={ns} iter {it}: {ms:.3f} ms  {a.channels * a.samples / ms / 1e3:.2f} Msamples/s  "
+              f"{ab / ms / 1e6:.1f} GB/s algorithmic")
+    sys.exit(0)
+if a.op == "istft":
+    Sx = torch.empty((a.channels, nfq, nfr), dtype=torch.complex64, device="cuda")
+    eng.stft(x, win, a.n_fft, a.hop, out=Sx)
+    xr = torch.empty((a.channels, a.samples), dtype=torch.float32, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(a.iters):
+        ev0.record()
+        xr = eng.istft(Sx, win, a.n_fft, a.hop, N=a.samples)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        ab = a.channels * (4 * a.samples + 8 * nfq * nfr)
+        err = float((xr - x).abs().max() / x.abs().max())
+        print(f"istft iter {it}: {ms:.3f} ms (kernel {eng.ctx.last_kernel_ms():.3f})  {a.channels * a.samples / ms / 1e3:.1f} Msamples/s  "
+              f"{ab / ms / 1e6:.1f} GB/s algorithmic  roundtrip max err {err:.2e}")
+    sys.exit(0)
 out = torch.empty((a.channels, nfq, nfr), dtype=torch.complex64, device="cuda")
 torch.cuda.synchronize()
 for it in range(a.iters):
