@@ -16,12 +16,20 @@ static FftPlanHost fft_plan(int log2L) {
     p.log2T = 0;
     return p;
   }
-  p.npass = (log2L + 6) / 7;
-  int left = log2L;
-  for (int i = 0; i < p.npass; ++i) {
-    const int rem = p.npass - i;
-    p.r[i] = (left + rem - 1) / rem;
-    left -= p.r[i];
+  // 7-bit passes first (fft128_pass_kernel: register butterflies), the remainder in one or two
+  // generic passes of >= 4 bits at the end (their Ns is then >= 128 >= T)
+  int n7 = log2L / 7, rem = log2L - 7 * n7;
+  p.npass = 0;
+  if (rem == 0) {
+    for (int i = 0; i < n7; ++i) p.r[p.npass++] = 7;
+  } else if (rem >= 4) {
+    for (int i = 0; i < n7; ++i) p.r[p.npass++] = 7;
+    p.r[p.npass++] = rem;
+  } else {
+    for (int i = 0; i < n7 - 1; ++i) p.r[p.npass++] = 7;
+    const int two = 7 + rem;  // 8..10 bits in two generic passes
+    p.r[p.npass++] = (two + 1) / 2;
+    p.r[p.npass++] = two / 2;
   }
   p.log2T = 5;
   return p;
@@ -73,11 +81,16 @@ static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int
     float2* o = last ? base.out : ((i & 1) ? ws1 : ws0);
     P.out = o;
     const int R = 1 << P.r, T = 1 << P.log2T;
-    const size_t smem = (size_t)2 * R * T * sizeof(float2);
     dim3 grid((unsigned)(L / ((int64_t)R * T)), (unsigned)rows);
-    SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fft_pass_kernel<<<grid, 256, smem, ctx->stream>>>(P);
-    SSQ_TRY(ssq_check_launch(ctx, "fft_pass_kernel"));
+    if (P.r == 7 && P.log2T == 5 && (log2Ns == 0 || log2Ns >= 5) && !getenv("SSQ_NO_FFT128")) {
+      fft128_pass_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+      SSQ_TRY(ssq_check_launch(ctx, "fft128_pass_kernel"));
+    } else {
+      const size_t smem = (size_t)2 * R * T * sizeof(float2);
+      SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fft_pass_kernel<<<grid, 256, smem, ctx->stream>>>(P);
+      SSQ_TRY(ssq_check_launch(ctx, "fft_pass_kernel"));
+    }
     cur_in = o;
     log2Ns += P.r;
   }
@@ -185,6 +198,13 @@ static ssq_status cwt_prepare(ssq_ctx* ctx, const CwtCall& c, int* log2L, FftPla
   SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft0, (size_t)c.channels * L * sizeof(float2)));
   *xhat = (float2*)ctx->ws_fft0.p;
   *max_rows = std::max<int64_t>(1, std::min<int64_t>(32768, ((int64_t)1 << 31) / (L * 8)));
+  if (pl->npass > 1) {
+    // multi-pass rows: keep the ping-pong workspaces of one batch inside L2 (126 MB) so that the
+    // intermediate passes never reach HBM; the same addresses are rewritten by the next batch
+    int64_t budget = (int64_t)2048 << 20;  // bytes per workspace (SSQ_CWT_WS_MB to experiment with L2-resident batches)
+    if (const char* e = getenv("SSQ_CWT_WS_MB")) budget = (int64_t)std::max(1, atoi(e)) << 20;
+    *max_rows = std::max<int64_t>(1, std::min<int64_t>(*max_rows, budget / (L * 8)));
+  }
   *ws0 = *ws1 = nullptr;
   if (pl->npass > 1) {
     const int64_t total_rows = std::max<int64_t>(c.channels, c.channels * c.ns * 2);
@@ -335,7 +355,7 @@ extern "C" ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int6
   }
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
-  ctx->last_kernel = "fft_pass_kernel+ssq_cwt_reassign_kernel";
+  ctx->last_kernel = "fft128_pass_kernel+ssq_cwt_reassign_kernel";
   return SSQ_OK;
 }
 

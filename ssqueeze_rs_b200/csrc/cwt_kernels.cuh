@@ -15,6 +15,7 @@
 // unpad, de-normalisation constant), so Wx is written exactly once.
 #pragma once
 #include "ssq_common.cuh"
+#include "stft_fast.cuh"
 
 struct FftPass {
   const float2* in;   // [rows, L] (unused by the first pass' functor loads)
@@ -192,6 +193,149 @@ __global__ void __launch_bounds__(256) fft_pass_kernel(const FftPass P) {
 }
 
 // ------------------------------------------------------------------------------------
+// Radix-128 pass, register butterflies (the fast path of every 7-bit pass):
+// CTA = 128 (t) x 32 (adjacent columns j); thread (c = tid & 31, g = tid >> 5) loads
+// t = g + 8 u (u = 0..15; each load is a 256 B run across the warp), does the 16-point DFT
+// over u in registers, multiplies by W_128^{g k1}, exchanges once through shared memory,
+// then (c, h) does the two 8-point DFTs over g for k1 in {h, h + 8}:
+//   Y[k1 + 16 k2] = sum_g W_8^{g k2} W_128^{g k1} sum_u x[g + 8 u] W_16^{u k1}.
+// The inverse transform is conj(forward(conj)): conjugation is folded into load and store.
+// Requires log2Ns == 0 (first pass; output block is transposed through shared memory so the
+// CTA writes 32 KB contiguously) or Ns >= 32 (outputs of adjacent columns are adjacent).
+// grid: (L / 4096, rows), 256 threads, 33,024 B static shared memory.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void fft4_fwd(float2& a, float2& b, float2& c, float2& d) {
+  const float2 apc = caddf(a, c), amc = csubf(a, c), bpd = caddf(b, d), bmd = csubf(b, d);
+  a = caddf(apc, bpd);
+  b = make_float2(amc.x + bmd.y, amc.y - bmd.x);  // amc - i bmd
+  c = csubf(apc, bpd);
+  d = make_float2(amc.x - bmd.y, amc.y + bmd.x);  // amc + i bmd
+}
+
+// in: v[u], u = 0..15; out: v[a + 4 b] = X[a + 4 b] (natural order)
+__device__ __forceinline__ void fft16_fwd(float2 (&v)[16]) {
+  const float C1 = 0.92387953251128673848f, S1 = 0.38268343236508978178f, H = 0.70710678118654752440f;
+  // step 1: 4-point DFTs over u1 of v[u0 + 4 u1] -> v[u0 + 4 a]
+#pragma unroll
+  for (int u0 = 0; u0 < 4; ++u0) fft4_fwd(v[u0], v[u0 + 4], v[u0 + 8], v[u0 + 12]);
+  // step 2: twiddles W_16^{u0 a} on v[u0 + 4 a]
+  v[5] = cmulf(v[5], make_float2(C1, -S1));    // u0=1,a=1: W^1
+  v[9] = cmulf(v[9], make_float2(H, -H));      // u0=1,a=2: W^2
+  v[13] = cmulf(v[13], make_float2(S1, -C1));  // u0=1,a=3: W^3
+  v[6] = cmulf(v[6], make_float2(H, -H));      // u0=2,a=1: W^2
+  v[10] = make_float2(v[10].y, -v[10].x);      // u0=2,a=2: W^4 = -i
+  v[14] = cmulf(v[14], make_float2(-H, -H));   // u0=2,a=3: W^6
+  v[7] = cmulf(v[7], make_float2(S1, -C1));    // u0=3,a=1: W^3
+  v[11] = cmulf(v[11], make_float2(-H, -H));   // u0=3,a=2: W^6
+  v[15] = cmulf(v[15], make_float2(-C1, S1));  // u0=3,a=3: W^9
+  // step 3: 4-point DFTs over u0 for each a: X[a + 4 b] lands in v[4 a + b]
+#pragma unroll
+  for (int a = 0; a < 4; ++a) fft4_fwd(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3]);
+  // reorder v[4 a + b] -> v[a + 4 b]
+  float2 t;
+  t = v[1]; v[1] = v[4]; v[4] = t;
+  t = v[2]; v[2] = v[8]; v[8] = t;
+  t = v[3]; v[3] = v[12]; v[12] = t;
+  t = v[6]; v[6] = v[9]; v[9] = t;
+  t = v[7]; v[7] = v[13]; v[13] = t;
+  t = v[11]; v[11] = v[14]; v[14] = t;
+}
+
+__device__ __forceinline__ float2 tw_fwd(const FftPass& P, int64_t e) {  // W_L^e, forward sign
+  const int lo = (int)(e & ((1 << P.tw_s) - 1));
+  const int hi = (int)(e >> P.tw_s);
+  return cmulf(__ldg(P.tw_lo + lo), __ldg(P.tw_hi + hi));
+}
+
+__global__ void __launch_bounds__(256) fft128_pass_kernel(const FftPass P) {
+  __shared__ float2 buf[32 * 129];
+  __shared__ float2 w128[128];  // W_128^m
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  if (threadIdx.x < 128) w128[threadIdx.x] = tw_fwd(P, (int64_t)threadIdx.x << (P.log2L - 7));
+  const int64_t L = (int64_t)1 << P.log2L;
+  const int64_t Q = L >> 7;
+  const int64_t Ns = (int64_t)1 << P.log2Ns;
+  const int row = blockIdx.y;
+  const int64_t j0 = (int64_t)blockIdx.x * 32, j = j0 + c;
+  const int64_t kk = j & (Ns - 1);
+  const int twshift = P.log2L - P.log2Ns - 7;  // W_{128 Ns}^e = W_L^(e << twshift)
+  const bool inv = P.sign > 0;
+
+  float2 v[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    float2 x = pass_load(P, row, j + (int64_t)(g + 8 * u) * Q);
+    if (inv) x.y = -x.y;
+    v[u] = x;
+  }
+  if (P.log2Ns > 0) {
+    // inter-pass twiddle W^{kk (g + 8u)} = W^{kk g} (W^{8 kk})^u: two table look-ups, then powers by
+    // repeated squaring / short products (every power is at most 4 multiplications deep)
+    const float2 wg = tw_fwd(P, (kk * g) << twshift);
+    float2 p[16];
+    p[1] = tw_fwd(P, (kk * 8) << twshift);
+    p[2] = cmulf(p[1], p[1]);
+    p[4] = cmulf(p[2], p[2]);
+    p[8] = cmulf(p[4], p[4]);
+    p[3] = cmulf(p[2], p[1]);
+    p[5] = cmulf(p[4], p[1]);
+    p[6] = cmulf(p[4], p[2]);
+    p[7] = cmulf(p[4], p[3]);
+#pragma unroll
+    for (int u = 9; u < 16; ++u) p[u] = cmulf(p[8], p[u - 8]);
+    v[0] = cmulf(v[0], wg);
+#pragma unroll
+    for (int u = 1; u < 16; ++u) v[u] = cmulf(v[u], cmulf(p[u], wg));
+  }
+  fft16_fwd(v);  // v[k1] = sum_u x[g + 8u] W_16^{u k1}
+  __syncthreads();  // w128 ready
+  if (g) {
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmulf(v[k1], w128[(g * k1) & 127]);
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) buf[(k1 * 8 + g) * 32 + c] = v[k1];
+  __syncthreads();
+  float2 a[8], b[8];
+#pragma unroll
+  for (int gg = 0; gg < 8; ++gg) {
+    a[gg] = buf[(g * 8 + gg) * 32 + c];        // k1 = h = g
+    b[gg] = buf[((g + 8) * 8 + gg) * 32 + c];  // k1 = h + 8
+  }
+  fft8_fwd(a);  // a[k2] = Y[g + 16 k2]
+  fft8_fwd(b);  // b[k2] = Y[g + 8 + 16 k2]
+  if (inv) {
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      a[k2].y = -a[k2].y;
+      b[k2].y = -b[k2].y;
+    }
+  }
+  if (P.log2Ns == 0) {
+    // out index = j * 128 + k: transpose so that the CTA writes its 4096 outputs contiguously
+    __syncthreads();
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      buf[c * 129 + g + 16 * k2] = a[k2];
+      buf[c * 129 + g + 8 + 16 * k2] = b[k2];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int e = threadIdx.x + 256 * i;
+      pass_store(P, row, (j0 << 7) + e, buf[(e >> 7) * 129 + (e & 127)]);
+    }
+  } else {
+    const int64_t base = ((j - kk) << 7) + kk;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      pass_store(P, row, base + (int64_t)(g + 16 * k2) * Ns, a[k2]);
+      pass_store(P, row, base + (int64_t)(g + 8 + 16 * k2) * Ns, b[k2]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // ssq_cwt reassignment (ssq_cwt.rs:116-222 + phase_cwt :15-47): one thread per time
 // column; the thread is the only writer of its Tx column, so the accumulation is
 // a plain read-modify-write in ascending scale order (the reference's order).
@@ -240,3 +384,4 @@ __global__ void ssq_cwt_reassign_kernel(const SsqCwtParams P) {
     *t = cur;
   }
 }
+

@@ -6,6 +6,7 @@
 #include "stft_kernels.cuh"
 #include "stft_fast.cuh"
 #include "stft_h32.cuh"
+#include "istft_h32.cuh"
 #include "cwt_kernels.cuh"
 
 #include <algorithm>
@@ -433,6 +434,51 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
   SSQ_TRY(devbuf_reserve(ctx, ctx->ws_misc, (size_t)channels * L * sizeof(float)));
   SSQ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_misc.p, 0, (size_t)channels * L * sizeof(float), ctx->stream));
 
+  if (n_fft == 512 && hop == 32 && !getenv("SSQ_NO_H32")) {
+    Istft32Params Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.Sx = (const float2*)d_Sx;
+    Q.channels = (int)channels;
+    Q.n_frames = n_frames;
+    Q.n_use = std::min<int64_t>(n_frames, max_hops);
+    Q.L = L;
+    Q.wa = T.wa;
+    Q.tw = T.tw;
+    Q.xacc = (float*)ctx->ws_misc.p;
+    SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (getenv("SSQ_ISTFT_RUNS")) {  // per-warp runs with register overlap-add (kept for comparison)
+      int run = 32;
+      const int64_t warps = (int64_t)ctx->num_sms * 2 * H32_WARPS;
+      while (run > 4 && ((Q.n_use + run - 1) / run) * channels < warps) run >>= 1;
+      Q.run = run;
+      Q.runs_per_channel = (Q.n_use + run - 1) / run;
+      Q.total_runs = Q.runs_per_channel * channels;
+      const size_t smem = ((size_t)72 + (size_t)H32_WARPS * (512 + 4 * I32_AS)) * sizeof(float2);
+      const int grid = (int)std::min<int64_t>((Q.total_runs + H32_WARPS - 1) / H32_WARPS, (int64_t)ctx->num_sms * 2);
+      SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(istft512_h32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      istft512_h32_kernel<<<grid, H32_WARPS * 32, smem, ctx->stream>>>(Q);
+      SSQ_TRY(ssq_check_launch(ctx, "istft512_h32_kernel"));
+      ctx->last_kernel = "istft512_h32_kernel";
+    } else {
+      Q.run = 32;
+      Q.runs_per_channel = (Q.n_use + 31) / 32;
+      Q.total_runs = Q.runs_per_channel * channels;
+      const size_t smem = ((size_t)72 + (size_t)32 * I32T_AS + (size_t)H32_WARPS * 512) * sizeof(float2);
+      const int grid = (int)std::min<int64_t>(Q.total_runs, (int64_t)ctx->num_sms * 2);
+      SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(istft512_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      istft512_tile_kernel<<<grid, H32_WARPS * 32, smem, ctx->stream>>>(Q);
+      SSQ_TRY(ssq_check_launch(ctx, "istft512_tile_kernel"));
+      ctx->last_kernel = "istft512_tile_kernel";
+    }
+    SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ev_valid = true;
+    dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
+    istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
+                                                      (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+    SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
+    return SSQ_OK;
+  }
+
   IstftParams P;
   memset(&P, 0, sizeof(P));
   P.Sx = (const float2*)d_Sx;
@@ -461,7 +507,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
   ctx->last_kernel = "istft_ola_kernel";
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->ev_valid = true;
-  dim3 g((unsigned)((n_out + 255) / 256), (unsigned)channels);
+  dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
   istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
                                                     (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
   SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));

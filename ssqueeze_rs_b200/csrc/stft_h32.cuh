@@ -115,15 +115,10 @@ struct H32Lane {
   float2 tw3a[7], tw3b[7];
 };
 
-template <int MODE, int SQZ>
-__device__ __forceinline__ void h32_frame(const StftParams& P, const H32Lane& L, float2* xch, float2* col,
-                                          float2 (&va)[8], float2 (&vb)[8]) {
+// 512-point forward DFT of one frame: inputs va[t] = z[lane + 64 t], vb[t] = z[lane + 32 + 64 t];
+// outputs va[m] = Z[lane + 64 m], vb[m] = Z[L.j2 + 64 m].  Two swizzled exchanges through xch.
+__device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2 (&va)[8], float2 (&vb)[8]) {
   const int lane = L.lane, j2 = L.j2;
-  float* sre = reinterpret_cast<float*>(xch);                          // [264] staging by SOURCE bin
-  float* sim = sre + 264;                                               // [264]
-  int* skey = reinterpret_cast<int*>(sre + 528);                        // [264]
-  unsigned char* tagA = reinterpret_cast<unsigned char*>(sre + 792);    // [264]
-  unsigned char* tagB = tagA + 264;                                     // [264]
   fft8_fwd(va);
   fft8_fwd(vb);
   {
@@ -171,6 +166,18 @@ __device__ __forceinline__ void h32_frame(const StftParams& P, const H32Lane& L,
   }
   fft8_fwd(va);  // va[m] = Z[lane + 64 m]
   fft8_fwd(vb);  // vb[m] = Z[j2 + 64 m]
+}
+
+template <int MODE, int SQZ>
+__device__ __forceinline__ void h32_frame(const StftParams& P, const H32Lane& L, float2* xch, float2* col,
+                                          float2 (&va)[8], float2 (&vb)[8]) {
+  const int lane = L.lane, j2 = L.j2;
+  float* sre = reinterpret_cast<float*>(xch);                          // [264] staging by SOURCE bin
+  float* sim = sre + 264;                                               // [264]
+  int* skey = reinterpret_cast<int*>(sre + 528);                        // [264]
+  unsigned char* tagA = reinterpret_cast<unsigned char*>(sre + 792);    // [264]
+  unsigned char* tagB = tagA + 264;                                     // [264]
+  h32_fft512(L, xch, va, vb);
 
   // ---- split + phase transform: lane owns bins lane+64m and j2+64m (and lane 0: 256) ------
   const bool l0 = L.l0;

@@ -166,3 +166,21 @@ def test_ssq_cwt_multipass_fft_and_batch():
     torch.cuda.synchronize()
     Wo, _, _ = O.cwt(xb[1].astype(np.float64), "gmw", sc, fs=1000.0)
     assert rel(W[1].cpu().numpy(), Wo) < RTOL
+
+
+@pytest.mark.parametrize("N", [9000, 40000, 100000, 700000])
+def test_cwt_fft_plans(N):
+    """pad_len 2^14 (passes 7,7), 2^16 (7,5,4), 2^18 (7,7,4), 2^21 (7,7,7 -- BASELINE config 3's length)."""
+    rs = _rs()
+    rng = np.random.default_rng(N)
+    t = np.arange(N) / 1000.0
+    x = np.sin(2 * np.pi * (3 * t + 0.5 * 0.02 * t ** 2)) + 0.3 * rng.standard_normal(N)
+    sc = np.array([2.0, 11.0, 97.0, 1500.0])
+    for wav in ("gmw", "morlet"):
+        Wx, _, dWx = rs.cwt(x, wav, sc, fs=1000.0, derivative=True)
+        Wo, _, dWo = O.cwt(x, wav, sc, fs=1000.0, derivative=True)
+        assert rel(Wx, Wo) < RTOL, (wav, rel(Wx, Wo))
+        assert rel(dWx, dWo) < RTOL, (wav, rel(dWx, dWo))
+    Wx, _, _ = rs.cwt(x, "gmw", sc, fs=1000.0, rpadded=True, padtype="zero")
+    Wo, _, _ = O.cwt(x, "gmw", sc, fs=1000.0, rpadded=True, padtype="zero")
+    assert rel(Wx, Wo) < RTOL

@@ -330,3 +330,43 @@ def test_full_size_properties_config2_slice():
     Tx2 = eng.ssq_stft(x * 2, win, 512, 32, fs)
     torch.cuda.synchronize()
     assert torch.equal(Tx2, Tx * 2)
+
+
+@pytest.mark.parametrize("N,wexp", [(20000, 1), (5000, 0), (777, 2), (100, 1), (4096 + 33, 1)])
+def test_istft_fast_path_512_32(N, wexp):
+    """n_fft=512 / hop=32 register overlap-add kernel against the oracle (irfft + OLA), on a
+    MODIFIED spectrum with non-zero imaginary DC / Nyquist parts (irfft ignores them)."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    rng = np.random.default_rng(N + wexp)
+    x = rng.standard_normal(N) * 7.0
+    win = np.hanning(514)[1:-1].copy()
+    So, _ = O.stft(x, 512, 32, win, "reflect")
+    So = So * (1 + 0.1 * rng.standard_normal(So.shape)) + 0.05j * rng.standard_normal(So.shape)
+    xr = rs.istft(So, win, n_fft=512, hop_len=32, N=N, win_exp=wexp)
+    assert "istft512" in _lib.default_context().last_kernel_name()
+    xo = O.istft(So, win, n_fft=512, hop_len=32, N=N, win_exp=wexp)
+    assert np.abs(xr - xo).max() < RTOL * np.abs(xo).max()
+    # fewer columns than the padded length allows, and more (extra columns are ignored: _stft.py:236)
+    for cols in (So.shape[1] - 3, So.shape[1]):
+        if cols < 1:
+            continue
+        S2 = np.ascontiguousarray(So[:, :cols])
+        xr = rs.istft(S2, win, n_fft=512, hop_len=32, N=N, win_exp=wexp)
+        xo = O.istft(S2, win, n_fft=512, hop_len=32, N=N, win_exp=wexp)
+        assert np.abs(xr - xo).max() < RTOL * max(np.abs(xo).max(), 1e-30)
+
+
+def test_istft_batched_roundtrip_fast_path():
+    import torch
+    from ssqueeze_rs_b200.batch import Engine
+    eng = Engine(0)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = torch.randn((37, 30001), generator=g, device="cuda") * 3
+    win = np.hanning(514)[1:-1].copy()
+    Sx = eng.stft(x, win, 512, 32)
+    xr = eng.istft(Sx, win, 512, 32, N=x.shape[1])
+    torch.cuda.synchronize()
+    assert eng.last_kernel_name().startswith("istft512")
+    assert float((xr - x).abs().max()) < 2e-5 * float(x.abs().max())
