@@ -37,8 +37,10 @@ N_FFT, HOP = 512, 32
 CHANNELS = 384
 SAMPLES = 1_800_000
 WORKLOAD = "ssq_stft 384ch x 1.8M samples (60 s @ 30 kHz) synthetic neural, n_fft=512 hop=32 hann reflect"
-# measured once with `ncu --set full` (profiles/), per launch of the dominant kernel; None until captured
-NCU_DRAM_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one 384-channel launch of the dominant kernel, from the ncu
+# pass over this same command (profiles/r1i_bench_launches.csv: 4.55 GB read + 45.43 GB written; the
+# algorithmic figure is 2.76 + 44.41 GB).  Only valid for the default workload; null otherwise.
+NCU_DRAM_BYTES_PER_LAUNCH = 49.98e9
 
 
 def algorithmic_bytes(channels, n, n_fft=N_FFT, hop=HOP):
@@ -280,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
     abytes = algorithmic_bytes(channels, n)
     achieved = abytes / (kms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel_ms": kms, "algorithmic_bytes_per_launch": abytes,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (channels, n) == (CHANNELS, SAMPLES) else None, "kernel_ms": kms, "algorithmic_bytes_per_launch": abytes,
                 "peak_source": peak_src, "kernel": eng.last_kernel_name()}
 
     # ---- e2e through the host-buffer C-ABI call --------------------------------

@@ -64,6 +64,7 @@ __device__ __forceinline__ float psihat(int wavelet, float w) {
   if (wavelet == SSQ_WAVELET_MORLET) {
     // cwt.rs:496-520: pi^-1/4 * sqrt2 * (exp(-(w-6)^2/2) - exp(-18) exp(-w^2/2)), w >= 0
     if (!(w >= 0.f)) return 0.f;
+    if (w > 14.5f) return 0.f;  // exp(-(w-6)^2/2) < 2e-16 of the peak: below fp32 resolution of any sum
     const float norm = 1.0622519320271968f;  // pi^-0.25 * sqrt(2)
     const float kexp = 1.5229979744712629e-08f;  // exp(-18)
     const float d = w - 6.f;
@@ -71,6 +72,9 @@ __device__ __forceinline__ float psihat(int wavelet, float w) {
   }
   // cwt.rs:522-541 (anything else is GMW): 2*exp(60 ln w - w^3), w > 0; normalised here
   if (!(w > 0.f)) return 0.f;
+  // outside (1.0, 4.5) the peak-normalised value is < 1e-17 (60 ln w - w^3 - 39.9 < -40): skip the
+  // transcendental evaluation, far below fp32 resolution of any sum it enters
+  if (w < 1.0f || w > 4.5f) return 0.f;
   return expf(60.f * logf(w) - w * w * w - (float)SSQ_GMW_LOGPEAK);
 }
 
