@@ -64,17 +64,20 @@ static ssq_status cwt_twiddles(ssq_ctx* ctx, int log2L, const float2** lo, const
 
 // Runs all passes of one batched FFT.  `base` carries the functor fields; the
 // first pass uses base.load_mode, the last base.store_mode; in between plain.
-static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int rows, float2* ws0, float2* ws1) {
+static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int rows, float2* ws0, float2* ws1,
+                          int skip = 0) {
   const int64_t L = (int64_t)1 << pl.log2L;
   int log2Ns = 0;
+  for (int i = 0; i < skip; ++i) log2Ns += pl.r[i];
+  base.up_shift = log2Ns;
   const float2* cur_in = nullptr;
-  for (int i = 0; i < pl.npass; ++i) {
+  for (int i = skip; i < pl.npass; ++i) {
     FftPass P = base;
     P.log2L = pl.log2L;
     P.log2Ns = log2Ns;
     P.r = pl.r[i];
     P.log2T = pl.log2T;
-    const bool first = (i == 0), last = (i == pl.npass - 1);
+    const bool first = (i == skip), last = (i == pl.npass - 1);
     if (!first) P.load_mode = 0;
     if (!last) P.store_mode = 0;
     P.in = cur_in;
@@ -83,7 +86,17 @@ static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int
     const int R = 1 << P.r, T = 1 << P.log2T;
     dim3 grid((unsigned)(L / ((int64_t)R * T)), (unsigned)rows);
     if (P.r == 7 && P.log2T == 5 && (log2Ns == 0 || log2Ns >= 5) && !getenv("SSQ_NO_FFT128")) {
-      fft128_pass_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+      // 64 columns per CTA (512 B runs) when the row is long enough; measured faster than 32
+      static const int tc_env = getenv("SSQ_FFT128_TC") ? atoi(getenv("SSQ_FFT128_TC")) : 64;
+      const int tc = (tc_env == 32 || L < (int64_t)128 * 64 || (log2Ns > 0 && log2Ns < 6)) ? 32 : 64;
+      dim3 g2((unsigned)(L / ((int64_t)128 * tc)), (unsigned)rows);
+      const size_t sm = (size_t)tc * 129 * sizeof(float2);
+      if (tc == 64) {
+        SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(fft128_pass_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        fft128_pass_kernel<64><<<g2, 512, sm, ctx->stream>>>(P);
+      } else {
+        fft128_pass_kernel<32><<<g2, 256, sm, ctx->stream>>>(P);
+      }
       SSQ_TRY(ssq_check_launch(ctx, "fft128_pass_kernel"));
     } else {
       const size_t smem = (size_t)2 * R * T * sizeof(float2);
@@ -139,6 +152,24 @@ static double cwt_denorm_constant(int wavelet) {
   return wavelet == SSQ_WAVELET_MORLET ? 1.0 : 2.0 * std::exp(SSQ_GMW_LOGPEAK);
 }
 
+// psi-hat(scale * xi) is exactly 0 in the kernel for scale * xi above the cut-off of psihat()
+// (cwt_kernels.cuh), i.e. for spectrum indices >= B = wmax L / (2 pi scale).  When B <= L/128 the
+// first radix-128 pass sees a single non-zero input per butterfly (t = 0): it is a broadcast,
+// its output at m is the spectrum at m >> 7, bit for bit.  When B <= L/128^2 the same holds for
+// the second pass.  Those passes are not run; the next pass reads the spectrum directly.
+static int cwt_skip_level(const CwtCall& c, const FftPlanHost& pl, int64_t si) {
+  if (pl.npass < 2 || pl.log2T != 5 || getenv("SSQ_NO_CWT_PRUNE")) return 0;
+  const double scale = c.scales[si];
+  if (!(scale > 0.0)) return 0;
+  const double wmax = (c.wavelet == SSQ_WAVELET_MORLET) ? 14.5 : 4.5;
+  const double L = (double)((int64_t)1 << pl.log2L);
+  const double B = wmax * L / (2.0 * SSQ_PI * scale) * (1.0 + 1e-4) + 2.0;
+  int lvl = 0;
+  if (pl.r[0] == 7 && B <= L / 128.0) lvl = 1;
+  if (lvl == 1 && pl.npass >= 3 && pl.r[1] == 7 && B <= L / 16384.0) lvl = 2;
+  return lvl;
+}
+
 // Shared driver: inverse transforms of rows [g0, g0+rows) in global (channel, scale, which) order.
 static ssq_status cwt_inverse_rows(ssq_ctx* ctx, const CwtCall& c, int log2L, const FftPlanHost& pl,
                                    const float2* lo, const float2* hi, int tw_s, const float2* xhat,
@@ -165,10 +196,15 @@ static ssq_status cwt_inverse_rows(ssq_ctx* ctx, const CwtCall& c, int log2L, co
   B.n1 = n1;
   B.out_scale = out_scale;
   B.l2_norm = (c.flags & SSQ_FLAG_L2_NORM) ? 1 : 0;
-  for (int64_t r0 = g0; r0 < g1; r0 += max_rows) {
-    const int rows = (int)std::min<int64_t>(max_rows, g1 - r0);
+  // rows are ordered (channel, scale, which): cut the range into runs of equal skip level
+  int64_t r0 = g0;
+  while (r0 < g1) {
+    const int lvl = cwt_skip_level(c, pl, (r0 / nd) % c.ns);
+    int64_t r1 = r0 + 1;
+    while (r1 < g1 && r1 - r0 < max_rows && cwt_skip_level(c, pl, (r1 / nd) % c.ns) == lvl) ++r1;
     B.row0 = r0;
-    SSQ_TRY(fft_run(ctx, pl, B, rows, ws0, ws1));
+    SSQ_TRY(fft_run(ctx, pl, B, (int)(r1 - r0), ws0, ws1, lvl));
+    r0 = r1;
   }
   return SSQ_OK;
 }

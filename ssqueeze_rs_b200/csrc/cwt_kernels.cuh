@@ -36,6 +36,7 @@ struct FftPass {
   int ns, nd;         // scales per channel, rows per scale (1: W only, 2: W and dW)
   int wavelet;
   float inv_dt;
+  int up_shift;       // mode 2: 7 * (number of leading passes skipped as broadcasts), see cwt_host.inl
   // ---- store functor ------------------------------------------------------------
   int store_mode;     // 0 plain, 1 final: scaled, unpadded rows to outW / outD
   float2* outW;       // [channels, ns, out_cols]
@@ -103,6 +104,9 @@ __device__ __forceinline__ float2 pass_load(const FftPass& P, int row, int64_t i
   const int64_t cs = g / P.nd;
   const int si = (int)(cs % P.ns);
   const int ch = (int)(cs / P.ns);
+  // band-limited rows: the skipped leading passes are broadcasts, their output at idx is the
+  // spectrum at idx >> up_shift (cwt_host.inl, cwt_skip_level)
+  idx >>= P.up_shift;
   // wavelets/base.rs:18-33 with scale 1: xi = 2 pi idx / L (idx <= L/2), 2 pi (idx - L) / L above
   const float xi = 6.283185307179586f * ((idx <= (L >> 1)) ? (float)idx : (float)(idx - L)) / (float)L;
   const float ps = psihat(P.wavelet, __ldg(P.scales + si) * xi);
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(256) fft_pass_kernel(const FftPass P) {
 // The inverse transform is conj(forward(conj)): conjugation is folded into load and store.
 // Requires log2Ns == 0 (first pass; output block is transposed through shared memory so the
 // CTA writes 32 KB contiguously) or Ns >= 32 (outputs of adjacent columns are adjacent).
-// grid: (L / 4096, rows), 256 threads, 33,024 B static shared memory.
+// grid: (L / (128 TC), rows), 8 TC threads, TC * 129 * 8 B dynamic shared memory.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void fft4_fwd(float2& a, float2& b, float2& c, float2& d) {
   const float2 apc = caddf(a, c), amc = csubf(a, c), bpd = caddf(b, d), bmd = csubf(b, d);
@@ -251,16 +255,17 @@ __device__ __forceinline__ float2 tw_fwd(const FftPass& P, int64_t e) {  // W_L^
   return cmulf(__ldg(P.tw_lo + lo), __ldg(P.tw_hi + hi));
 }
 
-__global__ void __launch_bounds__(256) fft128_pass_kernel(const FftPass P) {
-  __shared__ float2 buf[32 * 129];
+template <int TC>  // TC adjacent columns per CTA (32 or 64): TC * 8 B contiguous per global access, 8 * TC threads
+__global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
+  extern __shared__ float2 buf[];  // [TC * 129]
   __shared__ float2 w128[128];  // W_128^m
-  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = threadIdx.x % TC, g = threadIdx.x / TC;
   if (threadIdx.x < 128) w128[threadIdx.x] = tw_fwd(P, (int64_t)threadIdx.x << (P.log2L - 7));
   const int64_t L = (int64_t)1 << P.log2L;
   const int64_t Q = L >> 7;
   const int64_t Ns = (int64_t)1 << P.log2Ns;
   const int row = blockIdx.y;
-  const int64_t j0 = (int64_t)blockIdx.x * 32, j = j0 + c;
+  const int64_t j0 = (int64_t)blockIdx.x * TC, j = j0 + c;
   const int64_t kk = j & (Ns - 1);
   const int twshift = P.log2L - P.log2Ns - 7;  // W_{128 Ns}^e = W_L^(e << twshift)
   const bool inv = P.sign > 0;
@@ -298,13 +303,13 @@ __global__ void __launch_bounds__(256) fft128_pass_kernel(const FftPass P) {
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmulf(v[k1], w128[(g * k1) & 127]);
   }
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) buf[(k1 * 8 + g) * 32 + c] = v[k1];
+  for (int k1 = 0; k1 < 16; ++k1) buf[(k1 * 8 + g) * TC + c] = v[k1];
   __syncthreads();
   float2 a[8], b[8];
 #pragma unroll
   for (int gg = 0; gg < 8; ++gg) {
-    a[gg] = buf[(g * 8 + gg) * 32 + c];        // k1 = h = g
-    b[gg] = buf[((g + 8) * 8 + gg) * 32 + c];  // k1 = h + 8
+    a[gg] = buf[(g * 8 + gg) * TC + c];        // k1 = h = g
+    b[gg] = buf[((g + 8) * 8 + gg) * TC + c];  // k1 = h + 8
   }
   fft8_fwd(a);  // a[k2] = Y[g + 16 k2]
   fft8_fwd(b);  // b[k2] = Y[g + 8 + 16 k2]
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(256) fft128_pass_kernel(const FftPass P) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int e = threadIdx.x + 256 * i;
+      const int e = threadIdx.x + 8 * TC * i;
       pass_store(P, row, (j0 << 7) + e, buf[(e >> 7) * 129 + (e & 127)]);
     }
   } else {
