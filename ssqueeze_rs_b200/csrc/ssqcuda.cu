@@ -6,6 +6,7 @@
 #include "stft_kernels.cuh"
 #include "stft_fast.cuh"
 #include "stft_h32.cuh"
+#include "stft_h32r.cuh"
 #include "istft_h32.cuh"
 #include "cwt_kernels.cuh"
 
@@ -325,8 +326,12 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   bool done = false;
   if (!want_aux) {
-    ssq_status st = stft_h32_launch(ctx, P, &done);
+    ssq_status st = stft_h32r_launch(ctx, P, &done);
     if (st != SSQ_OK) return st;
+    if (!done) {
+      st = stft_h32_launch(ctx, P, &done);
+      if (st != SSQ_OK) return st;
+    }
     if (!done) {
       st = stft_fast_launch(ctx, P, &done);
       if (st != SSQ_OK) return st;

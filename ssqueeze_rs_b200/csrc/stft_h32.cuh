@@ -117,6 +117,8 @@ struct H32Lane {
 
 // 512-point forward DFT of one frame: inputs va[t] = z[lane + 64 t], vb[t] = z[lane + 32 + 64 t];
 // outputs va[m] = Z[lane + 64 m], vb[m] = Z[L.j2 + 64 m].  Two swizzled exchanges through xch.
+// ROT: the last butterfly of vb uses the conjugate kernel (see stft_h32r.cuh).
+template <bool ROT = false>
 __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2 (&va)[8], float2 (&vb)[8]) {
   const int lane = L.lane, j2 = L.j2;
   fft8_fwd(va);
@@ -159,6 +161,22 @@ __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2
     vb[t] = xch[(j2 ^ (8 * (t & 1))) + 64 * t];
   }
   __syncwarp();
+  if (ROT) {
+    // rotated variant (stft_h32r.cuh): the partner butterfly's twiddles are the conjugates of tw3a
+    // (W^{t (512 - e_a)}), except for lane 0 whose partner is j = 32: W^{480 t} = conj(W_16^t)
+    const float C1 = 0.92387953251128673848f, S1 = 0.38268343236508978178f, H = 0.70710678118654752440f;
+    const float2 w16[7] = {{C1, -S1}, {H, -H}, {S1, -C1}, {0.f, -1.f}, {-S1, -C1}, {-H, -H}, {-C1, -S1}};
+#pragma unroll
+    for (int t = 1; t < 8; ++t) {
+      const float2 wa = L.tw3a[t - 1];
+      va[t] = cmulf(va[t], wa);
+      const float2 wb = L.l0 ? w16[t - 1] : wa;
+      vb[t] = make_float2(vb[t].x * wb.x + vb[t].y * wb.y, vb[t].y * wb.x - vb[t].x * wb.y);  // vb * conj(wb)
+    }
+    fft8_fwd(va);
+    fft8_inv(vb);
+    return;
+  }
 #pragma unroll
   for (int t = 1; t < 8; ++t) {
     va[t] = cmulf(va[t], L.tw3a[t - 1]);

@@ -1,0 +1,302 @@
+// stft_h32r.cuh -- "rotated" variant of the n_fft = 512 / hop = 32 kernel: the item staging
+// (transposition of the 257 (bin, value) items through shared memory: 48 wavefronts per
+// frame on the binding L1TEX data pipe) is removed.
+//
+// The reassignment needs, in every step, 32 source bins that are far apart (>= 8 bins:
+// neighbouring sources often map to the SAME destination bin and would collide).  After a
+// plain stage 3 lane l holds Z[l + 64 m] in register m: in step m the warp would hold 32
+// CONSECUTIVE bins.  Rotating the last butterfly fixes that for free:
+//   va'[r] = Z[l + 64 ((r + rho) & 7)],  rho = l & 7:  fold W_8^{t rho} into the stage-3
+//            twiddle, i.e. use W_512^{t (l + 64 rho)};
+//   vb'[r] = Z[512 - (l + 64 ((r + rho) & 7))]: the partner butterfly j2 = 64 - l run with the
+//            CONJUGATE kernel on twiddles W_512^{t (j2 + 64 (7 - rho))}  (out_b[(7 - rho - r) & 7]).
+// Register pair r of lane l is then the conjugate pair (Z[k_a], Z[512 - k_a]),
+// k_a = l + 64 ((r + rho) & 7): it yields the ONE source bin k = min(k_a, 512 - k_a); in step r
+// lanes with equal rho are 8 bins apart and the others >= 33 apart (a few lane pairs 1-7).
+// Swapping the roles of the pair only flips the signs of Im Sx and Re V, so the item is
+// computed from (va'[r], vb'[r]) as is and the sign is carried by the signed source bin
+// skf[r] = +-k:  |k - q| = |skf - q0|.  Lane 0 (butterflies j = 0 and 32, both self-paired)
+// picks its pairs by static register indices.
+// Accumulation order inside a bin is no longer ascending in k (rounding-level difference to
+// the reference); it is fixed by the schedule, so results stay run-to-run identical.
+#pragma once
+#include "stft_h32.cuh"
+
+#define H32R_AS 261  // column stride (float2): bin k at k + (k >> 6) (max 260); odd
+
+__device__ __forceinline__ int h32r_phys(int k) { return k + (k >> 6); }
+
+struct H32RItem {
+  int kb;
+  float vre, vim;
+};
+
+// Pair (A, B) = (Z[k_a], Z[512 - k_a]) -> item of source bin |skf|.  sign(skf) < 0: roles swapped.
+template <int MODE, int SQZ>
+__device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float2* col, float skf, float2 A, float2 B) {
+  H32RItem it;
+  const unsigned sgn = __float_as_uint(skf) & 0x80000000u;
+  const float c = A.x + B.x, d0 = A.y - B.y;  // 2 Re Sx, +-2 Im Sx
+  if (MODE == 1) {
+    const int k = (int)fabsf(skf);
+    col[h32r_phys(k)] = make_float2(0.5f * c, __uint_as_float(__float_as_uint(0.5f * d0) ^ sgn));
+    it.kb = -1;
+    it.vre = it.vim = 0.f;
+    return it;
+  }
+  const float a = A.y + B.y, b0 = B.x - A.x;  // 2 V (Re with the swap sign)
+  const float den = fmaf(c, c, d0 * d0);
+  const float num0 = fmaf(b0, c, -a * d0);
+  const float q0 = num0 * rcp_approx(den);
+  const float binf = fabsf(fmaf(-q0, P.cphase, skf));
+  const float r = ceilf(binf - 0.5f);
+  it.kb = (int)fminf(fmaxf(r, 0.f), 256.f);  // fmaxf(NaN, 0) = 0 -> bin 0 like the reference
+  if (den < P.gate2) it.kb = -1;              // |Sx| < gamma (ssq_stft.rs:23): dropped
+  if (SQZ == SSQ_SQUEEZE_LEBESGUE) {
+    it.vre = P.leb_val;
+    it.vim = 0.f;
+  } else {
+    it.vre = c * P.tx_scale;
+    it.vim = __uint_as_float(__float_as_uint(d0 * P.tx_scale) ^ sgn);
+  }
+  return it;
+}
+
+__device__ __noinline__ void h32r_collision(float2* col, unsigned char* T, int kb, float vre, float vim, bool mine,
+                                            int lane) {
+  const bool on = kb >= 0;
+  {  // tonal frames: every active lane aims at the same bin -> one shuffle reduction, one add
+    const unsigned act = __ballot_sync(0xffffffffu, on);
+    const int first = __ffs(act) - 1;
+    const int kb0 = __shfl_sync(0xffffffffu, kb, first);
+    if (__all_sync(0xffffffffu, !on || kb == kb0)) {
+      float sr = on ? vre : 0.f, si = on ? vim : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+      }
+      if (lane == first) smem_rmw_add(col + h32r_phys(kb0), sr, si);
+      return;
+    }
+  }
+  if (on && !mine) T[kb] = 0xFF;
+  __syncwarp();
+  const bool contended = on && T[kb] == 0xFF;
+  if (on && !contended) smem_rmw_add(col + h32r_phys(kb), vre, vim);
+  unsigned m = __ballot_sync(0xffffffffu, contended);
+  while (m) {  // contended lanes one at a time, ascending lane order (deterministic)
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    if (lane == src) smem_rmw_add(col + h32r_phys(kb), vre, vim);
+    __syncwarp();
+  }
+}
+
+template <int MODE, int SQZ>
+// skf0: signed source bin of step 0; wrapd: increment applied instead of +64 after the step whose
+// source lies in [192, 256) (lanes >= 1: k_a jumps to the mirrored half, -448; lane 0: 192 -> 32).
+__device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L, float skf0, float wrapd, float2* xch,
+                                           float2* col, float2 (&va)[8], float2 (&vb)[8]) {
+  const int lane = L.lane;
+  const bool l0 = L.l0;
+  unsigned char* tagA = reinterpret_cast<unsigned char*>(xch);  // tags alias the exchange buffer
+  unsigned char* tagB = tagA + 264;
+  h32_fft512<true>(L, xch, va, vb);
+  __syncwarp();  // stage-3 reads done before the tags overwrite the buffer
+
+  // pair of step r: lanes >= 1 (va[r], vb[r]); lane 0: r < 4: (va[r], va[(8-r)&7]), r >= 4: (vb[11-r], vb[r-4])
+#define H32R_PAIR(r, A, B)                                   \
+  float2 A = va[r], B = vb[r];                               \
+  if (l0) {                                                  \
+    A = (r) < 4 ? va[r] : vb[(11 - (r)) & 7];                \
+    B = (r) < 4 ? va[(8 - (r)) & 7] : vb[((r)-4) & 7];       \
+  }
+
+  H32RItem cur;
+  float skf = skf0;
+  {
+    H32R_PAIR(0, A, B)
+    cur = h32r_item<MODE, SQZ>(P, col, skf, A, B);
+  }
+  if (MODE == 0) {
+    if (cur.kb >= 0) tagA[cur.kb] = (unsigned char)lane;
+    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    H32RItem nxt;
+    nxt.kb = -1;
+    nxt.vre = nxt.vim = 0.f;
+    if (r < 7) {  // next item's arithmetic overlaps this step's tag / accumulator latency
+      skf += (skf >= 192.f) ? wrapd : 64.f;
+      H32R_PAIR(r + 1, A, B)
+      nxt = h32r_item<MODE, SQZ>(P, col, skf, A, B);
+    }
+    if (MODE == 0) {
+      unsigned char* T = (r & 1) ? tagB : tagA;
+      unsigned char* Tn = (r & 1) ? tagA : tagB;
+      const bool on = cur.kb >= 0;
+      const bool mine = !on || T[cur.kb] == (unsigned char)lane;
+      if (__all_sync(0xffffffffu, mine)) {
+        if (on) smem_rmw_add(col + h32r_phys(cur.kb), cur.vre, cur.vim);
+      } else {
+        h32r_collision(col, T, cur.kb, cur.vre, cur.vim, mine, lane);
+      }
+      if (r < 7 && nxt.kb >= 0) Tn[nxt.kb] = (unsigned char)lane;
+      __syncwarp();
+    }
+    cur = nxt;
+  }
+#undef H32R_PAIR
+  // bin 256 = Z[256] of lane 0 (va[4], self-paired): last, outside the protocol
+  if (l0) {
+    const H32RItem it = h32r_item<MODE, SQZ>(P, col, 256.f, va[4], va[4]);
+    if (MODE == 0 && it.kb >= 0) smem_rmw_add(col + h32r_phys(it.kb), it.vre, it.vim);
+  }
+  __syncwarp();  // the tag area is the exchange buffer of the next frame
+}
+
+template <int MODE, int SQZ>
+__global__ void __launch_bounds__(H32_WARPS * 32, 2) ssq_stft512_h32r_kernel(const StftParams P) {
+  constexpr int N = 512, AS = H32R_AS, F = 32;
+  extern __shared__ float2 smem[];
+  float2* wtab = smem;          // [512] (w, dw*s)
+  float2* tw2tab = smem + N;    // [8][9]
+  float2* acc = smem + N + 72;  // [32][AS] the tile's Tx columns
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* xch = acc + F * AS + warp * N;  // 584 + 32 * 261 float2 is even: the float4 exchange rows stay 16 B aligned
+
+  for (int i = threadIdx.x; i < N; i += blockDim.x) wtab[i] = make_float2(P.win[i], P.dwin[i]);
+  if (threadIdx.x < 64)
+    tw2tab[(threadIdx.x >> 3) * 9 + (threadIdx.x & 7)] = P.tw[((threadIdx.x >> 3) * (threadIdx.x & 7) * 8) & (N - 1)];
+  for (int i = threadIdx.x; i < F * AS; i += blockDim.x) acc[i] = make_float2(0.f, 0.f);
+
+  // ---- per-lane constants ----------------------------------------------------------
+  H32Lane L;
+  L.lane = lane;
+  L.j2 = lane ? 64 - lane : 32;
+  L.tw2 = tw2tab + (lane & 7) * 9;
+  const int rho = lane & 7;
+  const int ea = lane + 64 * rho;  // va: W_512^{t (l + 64 rho)}; vb uses the conjugates (h32_fft512<true>)
+#pragma unroll
+  for (int t = 1; t < 8; ++t) {
+    L.tw3a[t - 1] = P.tw[(ea * t) & (N - 1)];
+    L.tw3b[t - 1] = make_float2(0.f, 0.f);  // unused
+  }
+  L.f1 = (lane >> 1) & 3;
+  L.rd1a = (lane >> 3) * 8 + ((((lane & 7) >> 1) ^ ((lane >> 4) & 3)) << 1) + (lane & 1);
+  L.rd1b = ((lane >> 3) + 4) * 8 + ((((lane & 7) >> 1) ^ (((lane >> 4) + 2) & 3)) << 1) + (lane & 1);
+  L.g2 = (lane >> 3) & 1;
+  L.wr2 = (lane >> 3) * 64 + (lane & 7);
+  L.lane_f = (float)lane;
+  L.j2_f = (float)L.j2;
+  L.l0 = (lane == 0);
+  // signed source bin of step r: skf_0, then +64 per step except once (see h32r_frame)
+  float skf0, wrapd;
+  if (lane == 0) {
+    skf0 = 0.f;
+    wrapd = -160.f;
+  } else {
+    const int ka = lane + 64 * rho;
+    skf0 = rho <= 3 ? (float)ka : (float)(ka - 512);
+    wrapd = -448.f;
+  }
+  __syncthreads();
+
+  // ---- the warp's frames of a tile: [f0, f0 + nfr), nfr in 0..4 ------------------------------
+  const float* xc = nullptr;
+  int64_t f0 = 0;
+  int nfr = 0;
+  bool inner = false;
+  float xw[16];
+  auto open_tile = [&](int64_t tile) {
+    const int ch = (int)(tile / P.tiles_per_channel);
+    f0 = (tile % P.tiles_per_channel) * F + 4 * warp;
+    nfr = (int)max((int64_t)0, min((int64_t)4, P.n_frames - f0));
+    xc = P.x + (size_t)ch * P.x_stride;
+    inner = f0 * 32 - P.left >= 0 && (f0 + 3) * 32 + N - 1 - P.left < P.n;
+    if (nfr > 0) {
+      const int64_t p = f0 * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        xw[j] = inner ? __ldg(xc + (p + 32 * j - P.left)) : stft_sample(xc, P.n, p + 32 * j, P.left, P.padtype);
+    }
+  };
+
+  int64_t tile = blockIdx.x;
+  if (tile < P.total_tiles) open_tile(tile);
+  for (; tile < P.total_tiles; tile += gridDim.x) {
+    const int tch = (int)(tile / P.tiles_per_channel);
+    const int64_t tf0 = (tile % P.tiles_per_channel) * F;
+    const int tnf = (int)min((int64_t)F, P.n_frames - tf0);
+    const int64_t next = tile + gridDim.x;
+    const int my_n = nfr;
+    if (my_n == 0 && next < P.total_tiles) open_tile(next);
+    for (int s = 0; s < my_n; ++s) {
+      float2 va[8], vb[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float2 w0 = wtab[lane + 64 * t], w1 = wtab[lane + 32 + 64 * t];
+        va[t] = make_float2(xw[2 * t] * w0.x, xw[2 * t] * w0.y);
+        vb[t] = make_float2(xw[2 * t + 1] * w1.x, xw[2 * t + 1] * w1.y);
+      }
+      if (s + 1 < my_n) {
+#pragma unroll
+        for (int j = 0; j < 15; ++j) xw[j] = xw[j + 1];
+        const int64_t p = (f0 + s + 1) * 32 + lane + 480;
+        xw[15] = inner ? __ldg(xc + (p - P.left)) : stft_sample(xc, P.n, p, P.left, P.padtype);
+      } else if (next < P.total_tiles) {
+        open_tile(next);
+      }
+      h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, xch, acc + (4 * warp + s) * AS, va, vb);
+    }
+    __syncthreads();
+    // ---- coalesced store: warp -> rows k = warp + 8 i at physical k + (k >> 6) = warp + 8 i + (i >> 3)
+    {
+      float2* a = acc + lane * AS + warp;
+      float2* g = P.out + ((size_t)tch * 257 + warp) * P.n_frames + tf0 + lane;
+      const size_t gstep = (size_t)8 * P.n_frames;
+      const bool ok = lane < tnf;
+#pragma unroll 1
+      for (int io = 0; io < 4; ++io) {
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          const float2 v = a[8 * ii];
+          if (MODE == 0) a[8 * ii] = make_float2(0.f, 0.f);
+          if (ok) *g = v;
+          g += gstep;
+        }
+        a += 65;
+      }
+      if (warp == 0) {  // row 256 at physical 260 (a has advanced by 4 * 65)
+        const float2 v = a[0];
+        if (MODE == 0) a[0] = make_float2(0.f, 0.f);
+        if (ok) *g = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static ssq_status stft_h32r_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
+  *done = false;
+  if (P.n_fft != 512 || P.hop != 32 || P.modulated || getenv("SSQ_NO_H32R")) return SSQ_OK;
+  P.F = 32;
+  P.acc_stride = H32R_AS;
+  P.tiles_per_channel = (P.n_frames + 31) / 32;
+  P.total_tiles = P.tiles_per_channel * P.channels;
+  const size_t smem = ((size_t)512 + 72 + (size_t)32 * H32R_AS + (size_t)H32_WARPS * 512) * sizeof(float2);
+  const int grid = (int)std::min<int64_t>(P.total_tiles, (int64_t)ctx->num_sms * 2);
+  const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
+  void (*k)(const StftParams) = P.mode == 1 ? ssq_stft512_h32r_kernel<1, 0>
+                                : leb       ? ssq_stft512_h32r_kernel<0, 1>
+                                            : ssq_stft512_h32r_kernel<0, 0>;
+  SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, H32_WARPS * 32, smem, ctx->stream>>>(P);
+  const char* name = P.mode == 1 ? "ssq_stft512_h32r_kernel<stft>" : "ssq_stft512_h32r_kernel<ssq>";
+  SSQ_TRY(ssq_check_launch(ctx, name));
+  ctx->last_kernel = name;
+  *done = true;
+  return SSQ_OK;
+}
