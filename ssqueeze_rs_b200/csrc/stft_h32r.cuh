@@ -157,15 +157,23 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
   __syncwarp();  // the tag area is the exchange buffer of the next frame
 }
 
-template <int MODE, int SQZ>
-__global__ void __launch_bounds__(H32_WARPS * 32, 2) ssq_stft512_h32r_kernel(const StftParams P) {
-  constexpr int N = 512, AS = H32R_AS, F = 32;
+// Edge tiles only (reflect / zero padding index map); kept out of line: the main loop has to fit the
+// instruction cache (the fully inlined version was 88 KB of SASS, 7 % of the issue slots starved).
+__device__ __noinline__ float h32r_edge_sample(const float* x, int64_t n, int64_t p, int left, int padtype) {
+  return stft_sample(x, n, p, left, padtype);
+}
+
+// NW warps per CTA (8: 32-frame tile, 2 CTAs per SM; 4: 16-frame tile, 4 CTAs per SM -- the same 16
+// warps per SM, half the barrier domain).
+template <int MODE, int SQZ, int NW>
+__global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(const StftParams P) {
+  constexpr int N = 512, AS = H32R_AS, F = 4 * NW;
   extern __shared__ float2 smem[];
   float2* wtab = smem;          // [512] (w, dw*s)
   float2* tw2tab = smem + N;    // [8][9]
   float2* acc = smem + N + 72;  // [32][AS] the tile's Tx columns
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float2* xch = acc + F * AS + warp * N;  // 584 + 32 * 261 float2 is even: the float4 exchange rows stay 16 B aligned
+  float2* xch = acc + F * AS + warp * N;  // 584 + F * 261 float2 is even (F = 16, 32): the float4 exchange rows stay 16 B aligned
 
   for (int i = threadIdx.x; i < N; i += blockDim.x) wtab[i] = make_float2(P.win[i], P.dwin[i]);
   if (threadIdx.x < 64)
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) ssq_stft512_h32r_kernel(con
   int nfr = 0;
   bool inner = false;
   float xw[16];
-  auto open_tile = [&](int64_t tile) {
+  auto open_tile = [&](int64_t tile) {  // single call site (see the loop): sets the warp's frames, loads frame f0's window
     const int ch = (int)(tile / P.tiles_per_channel);
     f0 = (tile % P.tiles_per_channel) * F + 4 * warp;
     nfr = (int)max((int64_t)0, min((int64_t)4, P.n_frames - f0));
@@ -218,85 +226,105 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) ssq_stft512_h32r_kernel(con
     inner = f0 * 32 - P.left >= 0 && (f0 + 3) * 32 + N - 1 - P.left < P.n;
     if (nfr > 0) {
       const int64_t p = f0 * 32 + lane;
+      if (inner) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        xw[j] = inner ? __ldg(xc + (p + 32 * j - P.left)) : stft_sample(xc, P.n, p + 32 * j, P.left, P.padtype);
+        for (int j = 0; j < 16; ++j) xw[j] = __ldg(xc + (p + 32 * j - P.left));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xw[j] = h32r_edge_sample(xc, P.n, p + 32 * j, P.left, P.padtype);
+      }
     }
   };
 
-  int64_t tile = blockIdx.x;
-  if (tile < P.total_tiles) open_tile(tile);
-  for (; tile < P.total_tiles; tile += gridDim.x) {
-    const int tch = (int)(tile / P.tiles_per_channel);
-    const int64_t tf0 = (tile % P.tiles_per_channel) * F;
-    const int tnf = (int)min((int64_t)F, P.n_frames - tf0);
+  // The loop starts one (virtual) tile early so that open_tile is inlined exactly once: the first
+  // pass only fetches the window of the CTA's first real tile.
+  for (int64_t tile = (int64_t)blockIdx.x - gridDim.x; tile < P.total_tiles; tile += gridDim.x) {
+    const bool real = tile >= 0;
+    const int tch = real ? (int)(tile / P.tiles_per_channel) : 0;
+    const int64_t tf0 = real ? (tile % P.tiles_per_channel) * F : 0;
+    const int tnf = real ? (int)min((int64_t)F, P.n_frames - tf0) : 0;
     const int64_t next = tile + gridDim.x;
-    const int my_n = nfr;
-    if (my_n == 0 && next < P.total_tiles) open_tile(next);
-    for (int s = 0; s < my_n; ++s) {
+    const int my_n = real ? nfr : 0;
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+      const bool active = s < my_n;
       float2 va[8], vb[8];
+      if (active) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float2 w0 = wtab[lane + 64 * t], w1 = wtab[lane + 32 + 64 * t];
-        va[t] = make_float2(xw[2 * t] * w0.x, xw[2 * t] * w0.y);
-        vb[t] = make_float2(xw[2 * t + 1] * w1.x, xw[2 * t + 1] * w1.y);
+        for (int t = 0; t < 8; ++t) {
+          const float2 w0 = wtab[lane + 64 * t], w1 = wtab[lane + 32 + 64 * t];
+          va[t] = make_float2(xw[2 * t] * w0.x, xw[2 * t] * w0.y);
+          vb[t] = make_float2(xw[2 * t + 1] * w1.x, xw[2 * t + 1] * w1.y);
+        }
       }
-      if (s + 1 < my_n) {
+      if (s == 3) {
+        if (next < P.total_tiles) open_tile(next);
+      } else if (s + 1 < my_n) {
 #pragma unroll
         for (int j = 0; j < 15; ++j) xw[j] = xw[j + 1];
         const int64_t p = (f0 + s + 1) * 32 + lane + 480;
-        xw[15] = inner ? __ldg(xc + (p - P.left)) : stft_sample(xc, P.n, p, P.left, P.padtype);
-      } else if (next < P.total_tiles) {
-        open_tile(next);
+        xw[15] = inner ? __ldg(xc + (p - P.left)) : h32r_edge_sample(xc, P.n, p, P.left, P.padtype);
       }
-      h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, xch, acc + (4 * warp + s) * AS, va, vb);
+      if (active) h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, xch, acc + (4 * warp + s) * AS, va, vb);
     }
+    if (!real) continue;
     __syncthreads();
-    // ---- coalesced store: warp -> rows k = warp + 8 i at physical k + (k >> 6) = warp + 8 i + (i >> 3)
+    // ---- coalesced store: thread -> (frame fr, row group v in 0..7); rows k = v + 8 i live at
+    //      physical k + (k >> 6) = v + 8 i + (i >> 3) = v + 65 io + 8 ii  (i = 8 io + ii)
     {
-      float2* a = acc + lane * AS + warp;
-      float2* g = P.out + ((size_t)tch * 257 + warp) * P.n_frames + tf0 + lane;
+      const int fr = threadIdx.x % F, v = threadIdx.x / F;
+      float2* a = acc + fr * AS + v;
+      float2* g = P.out + ((size_t)tch * 257 + v) * P.n_frames + tf0 + fr;
       const size_t gstep = (size_t)8 * P.n_frames;
-      const bool ok = lane < tnf;
+      const bool ok = fr < tnf;
 #pragma unroll 1
       for (int io = 0; io < 4; ++io) {
 #pragma unroll
         for (int ii = 0; ii < 8; ++ii) {
-          const float2 v = a[8 * ii];
+          const float2 val = a[8 * ii];
           if (MODE == 0) a[8 * ii] = make_float2(0.f, 0.f);
-          if (ok) *g = v;
+          if (ok) *g = val;
           g += gstep;
         }
         a += 65;
       }
-      if (warp == 0) {  // row 256 at physical 260 (a has advanced by 4 * 65)
-        const float2 v = a[0];
+      if (v == 0) {  // row 256 at physical 260 (a has advanced by 4 * 65)
+        const float2 val = a[0];
         if (MODE == 0) a[0] = make_float2(0.f, 0.f);
-        if (ok) *g = v;
+        if (ok) *g = val;
       }
     }
     __syncthreads();
   }
 }
 
-static ssq_status stft_h32r_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
-  *done = false;
-  if (P.n_fft != 512 || P.hop != 32 || P.modulated || getenv("SSQ_NO_H32R")) return SSQ_OK;
-  P.F = 32;
+template <int NW>
+static ssq_status stft_h32r_launch_nw(ssq_ctx* ctx, StftParams& P) {
+  constexpr int F = 4 * NW;
+  P.F = F;
   P.acc_stride = H32R_AS;
-  P.tiles_per_channel = (P.n_frames + 31) / 32;
+  P.tiles_per_channel = (P.n_frames + F - 1) / F;
   P.total_tiles = P.tiles_per_channel * P.channels;
-  const size_t smem = ((size_t)512 + 72 + (size_t)32 * H32R_AS + (size_t)H32_WARPS * 512) * sizeof(float2);
-  const int grid = (int)std::min<int64_t>(P.total_tiles, (int64_t)ctx->num_sms * 2);
+  const size_t smem = ((size_t)512 + 72 + (size_t)F * H32R_AS + (size_t)NW * 512) * sizeof(float2);
+  const int grid = (int)std::min<int64_t>(P.total_tiles, (int64_t)ctx->num_sms * (16 / NW));
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
-  void (*k)(const StftParams) = P.mode == 1 ? ssq_stft512_h32r_kernel<1, 0>
-                                : leb       ? ssq_stft512_h32r_kernel<0, 1>
-                                            : ssq_stft512_h32r_kernel<0, 0>;
+  void (*k)(const StftParams) = P.mode == 1 ? ssq_stft512_h32r_kernel<1, 0, NW>
+                                : leb       ? ssq_stft512_h32r_kernel<0, 1, NW>
+                                            : ssq_stft512_h32r_kernel<0, 0, NW>;
   SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, H32_WARPS * 32, smem, ctx->stream>>>(P);
+  k<<<grid, NW * 32, smem, ctx->stream>>>(P);
   const char* name = P.mode == 1 ? "ssq_stft512_h32r_kernel<stft>" : "ssq_stft512_h32r_kernel<ssq>";
   SSQ_TRY(ssq_check_launch(ctx, name));
   ctx->last_kernel = name;
+  return SSQ_OK;
+}
+
+static ssq_status stft_h32r_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
+  *done = false;
+  if (P.n_fft != 512 || P.hop != 32 || P.modulated || getenv("SSQ_NO_H32R")) return SSQ_OK;
+  static const int nw_env = getenv("SSQ_H32R_NW") ? atoi(getenv("SSQ_H32R_NW")) : 4;
+  if (nw_env == 4) SSQ_TRY(stft_h32r_launch_nw<4>(ctx, P));
+  else SSQ_TRY(stft_h32r_launch_nw<8>(ctx, P));
   *done = true;
   return SSQ_OK;
 }
