@@ -188,6 +188,27 @@ ssq_status ssq_ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_t channels,
                                  double fs, int padtype, int squeezing, double gamma,
                                  unsigned flags, float* Tx);
 
+/* ---- streaming ssq_stft over chunks of an interleaved recording ------------ */
+/* replaces the dask map_overlap caller of the reference (tests/stft_ssq_test.py:218-283:
+ * (samples, channels) chunks with depth n_fft, a per-channel Python loop inside each chunk).
+ * A stream is created for a recording of n_total samples x channels; every push hands over
+ * the next chunk as a DEVICE array [n_new, channels] (channels fastest) of int16 or float32,
+ * multiplied by `scale` on conversion, and writes the frames that became complete:
+ * d_Tx complex64 [channels, n_freqs, frames], frames = ssq_stream_frames_after(s, n_new)
+ * queried BEFORE the push.  Exact at chunk seams (padding only at the two ends of the
+ * recording): the concatenation over pushes equals ssq_ssq_stft_batch_f32 on the whole signal. */
+typedef struct ssq_stream ssq_stream;
+ssq_status ssq_stream_create(ssq_ctx* ctx, int64_t channels, int64_t n_total, int64_t max_chunk,
+                             const double* window, int64_t win_n, int n_fft, int hop, double fs,
+                             int padtype, int squeezing, double gamma, ssq_stream** out);
+void ssq_stream_destroy(ssq_stream* s);
+int64_t ssq_stream_total_frames(const ssq_stream* s);
+int64_t ssq_stream_frames_after(const ssq_stream* s, int64_t n_new);
+ssq_status ssq_stream_push_i16(ssq_stream* s, const int16_t* d_chunk, int64_t n_new, float scale,
+                               float* d_Tx, int64_t* frames_written);
+ssq_status ssq_stream_push_f32(ssq_stream* s, const float* d_chunk, int64_t n_new, float scale,
+                               float* d_Tx, int64_t* frames_written);
+
 /* pinned host memory helpers for the host-buffer path */
 ssq_status ssq_host_alloc(void** p, size_t bytes);
 void ssq_host_free(void* p);

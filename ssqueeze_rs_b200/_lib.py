@@ -68,6 +68,13 @@ SIGNATURES = {
                                       c_int, c_int, c_dbl, c_u32, c_vp, c_vp]),
     "ssq_ssq_stft_host_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int, c_int,
                                       c_dbl, c_u32, c_vp]),
+    "ssq_stream_create": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int, c_int, c_dbl,
+                                  C.POINTER(c_vp)]),
+    "ssq_stream_destroy": (None, [c_vp]),
+    "ssq_stream_total_frames": (c_i64, [c_vp]),
+    "ssq_stream_frames_after": (c_i64, [c_vp, c_i64]),
+    "ssq_stream_push_i16": (c_int, [c_vp, c_vp, c_i64, C.c_float, c_vp, C.POINTER(c_i64)]),
+    "ssq_stream_push_f32": (c_int, [c_vp, c_vp, c_i64, C.c_float, c_vp, C.POINTER(c_i64)]),
     "ssq_host_alloc": (c_int, [C.POINTER(c_vp), C.c_size_t]),
     "ssq_host_free": (None, [c_vp]),
 }

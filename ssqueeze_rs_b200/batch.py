@@ -173,6 +173,56 @@ class Engine:
         return (out, sf) if return_freqs else out
 
 
+class SsqStftStream:
+    """Streaming ssq_stft over chunks of an interleaved [samples, channels] recording (int16 or
+    float32 CUDA tensors): the B200 replacement of the dask `map_overlap` caller
+    (tests/stft_ssq_test.py:218-283 of the reference).  `push(chunk)` returns the frames that
+    became complete, complex64 [channels, n_freqs, frames]; concatenated along frames they equal
+    `Engine.ssq_stft` on the whole recording (no re-padding at chunk seams)."""
+
+    def __init__(self, engine: "Engine", channels, n_total, max_chunk, window, n_fft=512, hop_len=32, fs=1.0,
+                 padtype="reflect", squeezing="sum", gamma=None):
+        self.eng = engine
+        self.channels, self.n_freqs = int(channels), int(n_fft) // 2 + 1
+        w, wp = _wptr(window)
+        h = C.c_void_p()
+        st = load().ssq_stream_create(engine.ctx.handle, int(channels), int(n_total), int(max_chunk), wp, len(w),
+                                      int(n_fft), int(hop_len), float(fs), PAD.get(padtype, 0),
+                                      SQUEEZE.get(squeezing, 0), -1.0 if gamma is None else float(gamma), C.byref(h))
+        raise_status(st, engine.ctx.handle)
+        self._h = h
+
+    @property
+    def total_frames(self) -> int:
+        return int(load().ssq_stream_total_frames(self._h))
+
+    def push(self, chunk, scale=1.0):
+        import torch
+        assert chunk.is_cuda and chunk.dim() == 2 and chunk.shape[1] == self.channels and chunk.is_contiguous()
+        n_new = chunk.shape[0]
+        frames = int(load().ssq_stream_frames_after(self._h, n_new))
+        out = torch.empty((self.channels, self.n_freqs, max(frames, 0)), dtype=torch.complex64, device=chunk.device)
+        self.eng._bind_stream()
+        fw = C.c_int64()
+        fn = {torch.int16: load().ssq_stream_push_i16, torch.float32: load().ssq_stream_push_f32}[chunk.dtype]
+        st = fn(self._h, C.c_void_p(chunk.data_ptr()), n_new, float(scale),
+                C.c_void_p(out.data_ptr() if frames > 0 else 0), C.byref(fw))
+        raise_status(st, self.eng.ctx.handle)
+        assert fw.value == max(frames, 0)
+        return out
+
+    def close(self):
+        if self._h:
+            load().ssq_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def shard_channels(channels: int, n_devices: int):
     """Contiguous channel blocks: device g gets [g*C/G, (g+1)*C/G)."""
     return [(g * channels // n_devices, (g + 1) * channels // n_devices) for g in range(n_devices)]

@@ -274,6 +274,10 @@ struct StftCall {
   float2* aux_Sx;
   float2* aux_dSx;
   float* aux_w;
+  // streaming (ssq_stream_*): compute frames [frame0, frame0 + n_frames_call) of a recording of n
+  // samples; d_x is then a VIRTUAL base pointer indexed by global sample position
+  int64_t frame0 = 0;
+  int64_t n_frames_call = 0;
 };
 
 static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
@@ -285,7 +289,8 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
     return ssq_fail(ctx, SSQ_EPANIC, "empty input (n=%lld, channels=%lld): usize underflow in the reference",
                     (long long)c.n, (long long)c.channels);
   const int n_freqs = N / 2 + 1;
-  const int64_t n_frames = (c.n - 1) / c.hop + 1;
+  const bool streaming = c.n_frames_call > 0;
+  const int64_t n_frames = streaming ? c.n_frames_call : (c.n - 1) / c.hop + 1;
   StftTables T;
   SSQ_TRY(stft_tables(ctx, c.wfit, c.mode == 0 ? TAB_SSQ : TAB_STFT, 0, &T));
 
@@ -301,6 +306,7 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   P.log2n = ilog2_exact(N);
   P.is_pow2 = P.log2n >= 0;
   P.n_frames = n_frames;
+  P.frame0 = c.frame0;
   P.left = (N - 1) / 2;
   P.padtype = c.padtype == SSQ_PAD_ZERO ? SSQ_PAD_ZERO : SSQ_PAD_REFLECT;
   P.win = T.win;
@@ -328,11 +334,11 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   if (!want_aux) {
     ssq_status st = stft_h32r_launch(ctx, P, &done);
     if (st != SSQ_OK) return st;
-    if (!done) {
+    if (!done && !streaming) {  // the older kernels do not take a frame offset
       st = stft_h32_launch(ctx, P, &done);
       if (st != SSQ_OK) return st;
     }
-    if (!done) {
+    if (!done && !streaming) {
       st = stft_fast_launch(ctx, P, &done);
       if (st != SSQ_OK) return st;
     }
@@ -744,6 +750,189 @@ extern "C" ssq_status ssq_ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_
   if (st != SSQ_OK) return st;
   if (e != cudaSuccess) return ssq_fail(ctx, SSQ_ECUDA, "host-buffer pipeline: %s", cudaGetErrorString(e));
   return SSQ_OK;
+}
+
+// ===========================================================================
+// Streaming ssq_stft over a long recording delivered in chunks of interleaved
+// [samples, channels] int16 / float32 (replaces the dask
+// map_overlap caller of tests/stft_ssq_test.py:218-283).  Exact at chunk seams:
+// a frame is computed once every real sample it covers has arrived, padding
+// exists only at the two ends of the recording (the reference's caller re-pads
+// every chunk).  Concatenating the per-push outputs along frames equals the
+// whole-signal transform bit for bit.
+// ===========================================================================
+struct ssq_stream {
+  ssq_ctx* ctx;
+  int64_t channels, n_total, max_chunk, cap;
+  std::vector<double> wfit;
+  int n_fft, hop, left, padtype, squeezing;
+  double fs, gamma;
+  int64_t n_frames_total;
+  int64_t received = 0;   // samples pushed so far
+  int64_t origin = 0;     // global index of buf[.][0]
+  int64_t f_next = 0;     // next frame to compute
+  float* buf[2] = {nullptr, nullptr};  // [channels, cap] ping-pong (tail carried over by a D2D copy)
+  int cur = 0;
+};
+
+template <typename T>
+__global__ void deinterleave_kernel(const T* __restrict__ in, int64_t n_new, int64_t channels, float scale,
+                                    float* __restrict__ out, int64_t cap, int64_t pos) {
+  // in [n_new, channels] (channels fastest) -> out[ch * cap + pos + i]; 32 x 32 tile transpose
+  __shared__ float tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = i0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < n_new && c < channels) ? (float)in[i * channels + c] * scale : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t c = c0 + r, i = i0 + threadIdx.x;
+    if (c < channels && i < n_new) out[c * cap + pos + i] = tile[threadIdx.x][r];
+  }
+}
+
+static int64_t stream_frames_ready(const ssq_stream* s, int64_t received) {
+  if (received >= s->n_total) return s->n_frames_total;
+  const int64_t a = received - s->n_fft + s->left;  // last frame f with f*hop - left + n_fft - 1 < received
+  if (a < 0) return 0;
+  return std::min<int64_t>(s->n_frames_total, a / s->hop + 1);
+}
+
+extern "C" ssq_status ssq_stream_create(ssq_ctx* ctx, int64_t channels, int64_t n_total, int64_t max_chunk,
+                                        const double* window, int64_t win_n, int n_fft, int hop, double fs,
+                                        int padtype, int squeezing, double gamma, ssq_stream** out) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!out || !window || win_n < 1) return ssq_fail(ctx, SSQ_EINVAL, "NULL/empty argument");
+  *out = nullptr;
+  if (channels < 1 || n_total < 1 || max_chunk < 1) return ssq_fail(ctx, SSQ_EINVAL, "bad channels/n_total/max_chunk");
+  if (n_fft <= 0) n_fft = (int)std::min<int64_t>(n_total, 512);
+  if (n_fft < 2 || hop < 1) return ssq_fail(ctx, SSQ_EINVAL, "bad n_fft/hop");
+  if (win_n > n_fft)
+    return ssq_fail(ctx, SSQ_EINVAL, "Window length %lld cannot be greater than n_fft %d", (long long)win_n, n_fft);
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ssq_stream* s = new (std::nothrow) ssq_stream();
+  if (!s) return ssq_fail(ctx, SSQ_ENOMEM, "out of host memory");
+  s->ctx = ctx;
+  s->channels = channels;
+  s->n_total = n_total;
+  s->max_chunk = max_chunk;
+  s->wfit = ssqhost::fit_window(window, win_n, n_fft);
+  s->n_fft = n_fft;
+  s->hop = hop;
+  s->left = (n_fft - 1) / 2;
+  s->padtype = padtype;
+  s->squeezing = squeezing;
+  s->fs = fs;
+  s->gamma = gamma;
+  s->n_frames_total = (n_total - 1) / hop + 1;
+  s->cap = max_chunk + n_fft + hop + 32;
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaMalloc((void**)&s->buf[i], (size_t)channels * s->cap * sizeof(float));
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (s->buf[0]) cudaFree(s->buf[0]);
+      delete s;
+      return ssq_fail(ctx, SSQ_ENOMEM, "stream buffers (%lld x %lld floats): %s", (long long)channels,
+                      (long long)s->cap, cudaGetErrorString(e));
+    }
+  }
+  *out = s;
+  return SSQ_OK;
+}
+
+extern "C" void ssq_stream_destroy(ssq_stream* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (int i = 0; i < 2; ++i)
+    if (s->buf[i]) cudaFree(s->buf[i]);
+  delete s;
+}
+
+extern "C" int64_t ssq_stream_total_frames(const ssq_stream* s) { return s ? s->n_frames_total : 0; }
+
+extern "C" int64_t ssq_stream_frames_after(const ssq_stream* s, int64_t n_new) {
+  if (!s || n_new < 0) return 0;
+  const int64_t r = std::min<int64_t>(s->n_total, s->received + n_new);
+  return stream_frames_ready(s, r) - s->f_next;
+}
+
+template <typename T>
+static ssq_status stream_push(ssq_stream* s, const T* d_chunk, int64_t n_new, float scale, float* d_Tx,
+                              int64_t* frames_written) {
+  if (!s) return ssq_fail(nullptr, SSQ_EINVAL, "stream is NULL");
+  ssq_ctx* ctx = s->ctx;
+  if (frames_written) *frames_written = 0;
+  if (n_new < 0 || n_new > s->max_chunk) return ssq_fail(ctx, SSQ_EINVAL, "chunk of %lld samples (max %lld)", (long long)n_new, (long long)s->max_chunk);
+  if (s->received + n_new > s->n_total) return ssq_fail(ctx, SSQ_EINVAL, "more samples pushed than n_total");
+  if (n_new > 0 && !d_chunk) return ssq_fail(ctx, SSQ_EINVAL, "chunk is NULL");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t have = s->received - s->origin;
+  if (have + n_new > s->cap) return ssq_fail(ctx, SSQ_EINVAL, "internal: stream buffer overflow");
+  float* buf = s->buf[s->cur];
+  if (n_new > 0) {
+    dim3 g((unsigned)((n_new + 31) / 32), (unsigned)((s->channels + 31) / 32)), b(32, 8);
+    deinterleave_kernel<T><<<g, b, 0, ctx->stream>>>(d_chunk, n_new, s->channels, scale, buf, s->cap, have);
+    SSQ_TRY(ssq_check_launch(ctx, "deinterleave_kernel"));
+  }
+  s->received += n_new;
+  const int64_t f_end = stream_frames_ready(s, s->received);
+  const int64_t count = f_end - s->f_next;
+  if (count > 0) {
+    if (!d_Tx) return ssq_fail(ctx, SSQ_EINVAL, "d_Tx is NULL but %lld frames are ready", (long long)count);
+    StftCall c;
+    c.mode = 0;
+    c.d_x = buf - s->origin;  // virtual base: indexed by global sample position
+    c.channels = s->channels;
+    c.n = s->n_total;
+    c.x_stride = s->cap;
+    c.wfit = s->wfit;
+    c.n_fft = s->n_fft;
+    c.hop = s->hop;
+    c.fs = s->fs;
+    c.padtype = s->padtype;
+    c.squeezing = s->squeezing;
+    c.gamma = s->gamma;
+    c.flags = 0;
+    c.d_out = (float2*)d_Tx;
+    c.aux_Sx = nullptr;
+    c.aux_dSx = nullptr;
+    c.aux_w = nullptr;
+    c.frame0 = s->f_next;
+    c.n_frames_call = count;
+    SSQ_TRY(run_stft_family(ctx, c));
+    s->f_next = f_end;
+  }
+  if (frames_written) *frames_written = std::max<int64_t>(count, 0);
+  // carry over the samples the next frame still needs
+  if (s->f_next < s->n_frames_total) {
+    // the next frame starts at f_next*hop - left; frames that touch the right padding also read the
+    // reflected samples x[2n-2-o] >= n - n_fft, which may lie before their own start when hop is large
+    const int64_t want = std::min<int64_t>(std::max<int64_t>(0, s->f_next * s->hop - s->left),
+                                           std::max<int64_t>(0, s->n_total - s->n_fft));
+    const int64_t new_origin = std::max<int64_t>(s->origin, want);
+    if (new_origin > s->origin) {
+      const int64_t keep = s->received - new_origin;
+      float* nb = s->buf[s->cur ^ 1];
+      if (keep > 0)
+        SSQ_CUDA_TRY(ctx, cudaMemcpy2DAsync(nb, (size_t)s->cap * sizeof(float), buf + (new_origin - s->origin),
+                                            (size_t)s->cap * sizeof(float), (size_t)keep * sizeof(float),
+                                            (size_t)s->channels, cudaMemcpyDeviceToDevice, ctx->stream));
+      s->cur ^= 1;
+      s->origin = new_origin;
+    }
+  }
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_stream_push_i16(ssq_stream* s, const int16_t* d_chunk, int64_t n_new, float scale,
+                                          float* d_Tx, int64_t* frames_written) {
+  return stream_push<int16_t>(s, d_chunk, n_new, scale, d_Tx, frames_written);
+}
+extern "C" ssq_status ssq_stream_push_f32(ssq_stream* s, const float* d_chunk, int64_t n_new, float scale,
+                                          float* d_Tx, int64_t* frames_written) {
+  return stream_push<float>(s, d_chunk, n_new, scale, d_Tx, frames_written);
 }
 
 #include "cwt_host.inl"

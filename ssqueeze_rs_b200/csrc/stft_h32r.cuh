@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
     const int ch = (int)(tile / P.tiles_per_channel);
     f0 = (tile % P.tiles_per_channel) * F + 4 * warp;
     nfr = (int)max((int64_t)0, min((int64_t)4, P.n_frames - f0));
+    f0 += P.frame0;  // from here on f0 is the GLOBAL frame index (sample addressing only)
     xc = P.x + (size_t)ch * P.x_stride;
     inner = f0 * 32 - P.left >= 0 && (f0 + 3) * 32 + N - 1 - P.left < P.n;
     if (nfr > 0) {

@@ -42,6 +42,9 @@ struct StftParams {
   float2* aux_Sx;       // optional, same shape
   float2* aux_dSx;      // optional
   float* aux_w;         // optional (Hz, +inf where gated)
+  int64_t frame0;       // global index of local frame 0 (streaming: the call computes frames
+                        // [frame0, frame0 + n_frames) of a longer recording; x is then addressed by
+                        // GLOBAL sample index and n is the total length, see ssq_stream_* in ssqcuda.cu)
   int F;                // frames per tile
   int acc_stride;       // odd >= n_freqs
   int64_t tiles_per_channel, total_tiles;
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
 
     for (int fl = warp; fl < nf; fl += nw) {
       const int64_t frame = f0 + fl;
-      const int64_t start = frame * P.hop;
+      const int64_t start = (P.frame0 + frame) * P.hop;
       float2* A = work;
       float2* B = work + N;
       for (int n = lane; n < N; n += 32) {
