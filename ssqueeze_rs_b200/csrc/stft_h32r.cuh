@@ -1,4 +1,5 @@
-// stft_h32r.cuh -- "rotated" variant of the n_fft = 512 / hop = 32 kernel: the item staging
+// stft_h32r.cuh -- "rotated" variant of the n_fft = 512 kernel (hop = 32: register sliding window; any
+// other hop: per-frame reload): the item staging
 // (transposition of the 257 (bin, value) items through shared memory: 48 wavefronts per
 // frame on the binding L1TEX data pipe) is removed.
 //
@@ -165,7 +166,9 @@ __device__ __noinline__ float h32r_edge_sample(const float* x, int64_t n, int64_
 
 // NW warps per CTA (8: 32-frame tile, 2 CTAs per SM; 4: 16-frame tile, 4 CTAs per SM -- the same 16
 // warps per SM, half the barrier domain).
-template <int MODE, int SQZ, int NW>
+// SLIDE: hop == 32, the register sliding window (one new sample per lane and frame).  Otherwise any hop:
+// the 16 samples of every frame are (re)loaded, still a whole frame ahead of their use.
+template <int MODE, int SQZ, int NW, bool SLIDE>
 __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(const StftParams P) {
   constexpr int N = 512, AS = H32R_AS, F = 4 * NW;
   extern __shared__ float2 smem[];
@@ -224,9 +227,10 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
     nfr = (int)max((int64_t)0, min((int64_t)4, P.n_frames - f0));
     f0 += P.frame0;  // from here on f0 is the GLOBAL frame index (sample addressing only)
     xc = P.x + (size_t)ch * P.x_stride;
-    inner = f0 * 32 - P.left >= 0 && (f0 + 3) * 32 + N - 1 - P.left < P.n;
+    const int64_t hop = SLIDE ? 32 : P.hop;
+    inner = f0 * hop - P.left >= 0 && (f0 + 3) * hop + N - 1 - P.left < P.n;
     if (nfr > 0) {
-      const int64_t p = f0 * 32 + lane;
+      const int64_t p = f0 * hop + lane;
       if (inner) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) xw[j] = __ldg(xc + (p + 32 * j - P.left));
@@ -261,10 +265,21 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
       if (s == 3) {
         if (next < P.total_tiles) open_tile(next);
       } else if (s + 1 < my_n) {
+        if (SLIDE) {
 #pragma unroll
-        for (int j = 0; j < 15; ++j) xw[j] = xw[j + 1];
-        const int64_t p = (f0 + s + 1) * 32 + lane + 480;
-        xw[15] = inner ? __ldg(xc + (p - P.left)) : h32r_edge_sample(xc, P.n, p, P.left, P.padtype);
+          for (int j = 0; j < 15; ++j) xw[j] = xw[j + 1];
+          const int64_t p = (f0 + s + 1) * 32 + lane + 480;
+          xw[15] = inner ? __ldg(xc + (p - P.left)) : h32r_edge_sample(xc, P.n, p, P.left, P.padtype);
+        } else {
+          const int64_t p = (f0 + s + 1) * (int64_t)P.hop + lane;
+          if (inner) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xw[j] = __ldg(xc + (p + 32 * j - P.left));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xw[j] = h32r_edge_sample(xc, P.n, p + 32 * j, P.left, P.padtype);
+          }
+        }
       }
       if (active) h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, xch, acc + (4 * warp + s) * AS, va, vb);
     }
@@ -309,9 +324,15 @@ static ssq_status stft_h32r_launch_nw(ssq_ctx* ctx, StftParams& P) {
   const size_t smem = ((size_t)512 + 72 + (size_t)F * H32R_AS + (size_t)NW * 512) * sizeof(float2);
   const int grid = (int)std::min<int64_t>(P.total_tiles, (int64_t)ctx->num_sms * (16 / NW));
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
-  void (*k)(const StftParams) = P.mode == 1 ? ssq_stft512_h32r_kernel<1, 0, NW>
-                                : leb       ? ssq_stft512_h32r_kernel<0, 1, NW>
-                                            : ssq_stft512_h32r_kernel<0, 0, NW>;
+  void (*k)(const StftParams);
+  if (P.hop == 32)
+    k = P.mode == 1 ? ssq_stft512_h32r_kernel<1, 0, NW, true>
+        : leb       ? ssq_stft512_h32r_kernel<0, 1, NW, true>
+                    : ssq_stft512_h32r_kernel<0, 0, NW, true>;
+  else
+    k = P.mode == 1 ? ssq_stft512_h32r_kernel<1, 0, NW, false>
+        : leb       ? ssq_stft512_h32r_kernel<0, 1, NW, false>
+                    : ssq_stft512_h32r_kernel<0, 0, NW, false>;
   SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<grid, NW * 32, smem, ctx->stream>>>(P);
   const char* name = P.mode == 1 ? "ssq_stft512_h32r_kernel<stft>" : "ssq_stft512_h32r_kernel<ssq>";
@@ -322,7 +343,8 @@ static ssq_status stft_h32r_launch_nw(ssq_ctx* ctx, StftParams& P) {
 
 static ssq_status stft_h32r_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   *done = false;
-  if (P.n_fft != 512 || P.hop != 32 || P.modulated || getenv("SSQ_NO_H32R")) return SSQ_OK;
+  if (P.n_fft != 512 || P.modulated || getenv("SSQ_NO_H32R")) return SSQ_OK;
+  if (P.hop != 32 && getenv("SSQ_H32R_HOP32_ONLY")) return SSQ_OK;
   static const int nw_env = getenv("SSQ_H32R_NW") ? atoi(getenv("SSQ_H32R_NW")) : 4;
   if (nw_env == 4) SSQ_TRY(stft_h32r_launch_nw<4>(ctx, P));
   else SSQ_TRY(stft_h32r_launch_nw<8>(ctx, P));
