@@ -409,3 +409,47 @@ def test_fast_kernels_agree_and_are_deterministic():
         # identical bins -> only rounding differences; a handful of edge flips are tolerated
         assert float((d > 1e-4 * sc).float().mean()) < 1e-4, name
         assert float((outs[name][0].sum(dim=1) - ref.sum(dim=1)).abs().max()) < 2e-3 * sc, name
+
+
+def test_long_recording_config5_geometry():
+    """BASELINE config 5 geometry (10 min @ 30 kHz = 18 M samples per channel, 562 500 frames) on a
+    2-channel cut: 64-bit indexing, frames far into the recording against the oracle (a frame only
+    depends on its own 512 samples, so the oracle runs on a slice), and the column-sum property."""
+    import torch
+    from ssqueeze_rs_b200.batch import Engine
+    eng = Engine(0)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    ch, n = 2, 18_000_000
+    x = torch.randn((ch, n), generator=g, device="cuda") * 15
+    win = np.hanning(512)
+    fs = 30000.0
+    Tx = eng.ssq_stft(x, win, 512, 32, fs)
+    torch.cuda.synchronize()
+    assert Tx.shape == (ch, 257, 562_500)
+    for c, f_a in ((0, 0), (1, 280_000), (1, 562_500 - 64)):
+        a = 32 * f_a
+        xs = x[c, a:a + 32 * 64].cpu().numpy().astype(np.float64)
+        To, _ = O.ssq_stft(xs, win, n_fft=512, hop_len=32, fs=fs)
+        lo, hi = (0, 48) if f_a == 0 else ((16, 64) if f_a + 64 >= 562_500 else (16, 48))
+        got = Tx[c, :, f_a + lo:f_a + hi].cpu().numpy().astype(np.complex128)
+        _flip_tolerant_compare(got, To[:, lo:hi], max_bad_frac=4e-3)
+    Sx = eng.stft(x[1:2], win, 512, 32)
+    torch.cuda.synchronize()
+    dw = 0.5 * fs / 256
+    d = (Tx[1].sum(dim=0) - Sx[0].sum(dim=0) * dw).abs().max()
+    assert float(d) < 8e-3 * float(Sx.abs().max()) * dw
+
+
+def test_channel_sharder_matches_engine():
+    """Host-side multi-device path (one context + host thread per device, host gather only);
+    with one GPU the two 'devices' are two contexts on cuda:0."""
+    import torch
+    from ssqueeze_rs_b200.batch import ChannelSharder, Engine
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal((7, 20000)) * 5).astype(np.float32)
+    win = np.hanning(512)
+    ref = Engine(0).ssq_stft(torch.from_numpy(x).cuda(), win, 512, 32, 30000.0).cpu().numpy()
+    for devs in ([0], [0, 0], [0, 0, 0]):
+        out = ChannelSharder(devs).ssq_stft(x, win, 512, 32, 30000.0)
+        assert out.shape == ref.shape and np.array_equal(out, ref)
