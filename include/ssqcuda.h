@@ -147,6 +147,14 @@ ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet
                            int padtype, int squeezing, int maprange, double gamma,
                            unsigned flags, double* Tx, double* ssq_freqs);
 
+/* `icwt`: cwt.rs:548-718, a #[pyfunction] the reference module never registers.
+ * One-integral branch (:590-627, the default): x[j] = (2/adm) dj sum_i Re Wx[i,j] norm_i + x_mean.
+ * one_int == 0 (two-integral, FFTs of arbitrary length x_len) returns SSQ_EUNSUPPORTED.
+ * Wx complex128 [ns, n_cols] -> x float64 [x_len] (x_len <= 0: n_cols).  flags: SSQ_FLAG_L2_NORM. */
+ssq_status ssq_icwt_f64(ssq_ctx* ctx, const double* Wx, int64_t ns, int64_t n_cols, int wavelet,
+                        const double* scales, int one_int, int64_t x_len, double x_mean, unsigned flags,
+                        double* x);
+
 /* ---- batched throughput path (device buffers, fp32 / complex64) ---------- */
 /* replaces the per-channel Python loop around `_rs.ssq_stft`
  * (tests/stft_ssq_test.py:230-251).  d_x: [channels, n] fp32 with row stride
@@ -180,6 +188,11 @@ ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channel
                                  int64_t ns, double dt, int freq_dist, int padtype,
                                  int squeezing, int maprange, double gamma, unsigned flags,
                                  float* d_Tx, double* ssq_freqs);
+
+/* d_Wx complex64 [channels, ns, n_cols] -> d_x fp32 [channels, x_len] */
+ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_t channels, int64_t ns, int64_t n_cols,
+                              int wavelet, const double* scales, int one_int, int64_t x_len, double x_mean,
+                              unsigned flags, float* d_x);
 
 /* ---- batched path with HOST buffers (copies inside; synchronous) --------- */
 /* x: host fp32 [channels, n]; Tx: host complex64 [channels, n_freqs, n_frames] */

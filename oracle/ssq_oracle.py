@@ -493,3 +493,30 @@ def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=3
     if return_aux:
         return Tx, sf, dict(Wx=Wx, dWx=dWx, w=w, k=kk, scales=scales)
     return Tx, sf
+
+
+# --------------------------------------------------------------------------
+# icwt (cwt.rs:548-718, a #[pyfunction] the module never registers)
+# --------------------------------------------------------------------------
+def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_mean=0.0,
+         padtype="reflect", rpadded=False, l1_norm=True):
+    """cwt.rs:548-718.  Only the one-integral branch (:590-627, the default) is restated: the
+    two-integral branch needs FFTs of arbitrary length x_len and is not built (SSQ_EUNSUPPORTED)."""
+    Wx = np.asarray(Wx, dtype=np.complex128)
+    if scales is None:
+        raise ValueError("Scales must be provided")  # cwt.rs:572-575
+    scales = np.asarray(scales, dtype=np.float64)
+    n_scales, n_times = Wx.shape
+    adm = 0.776 if wavelet == "morlet" else 1.0       # cwt.rs:579-583
+    x_length = n_times if x_len is None else int(x_len)
+    if x_length > n_times:
+        raise IndexError("x_len > Wx.shape[1]: ndarray index out of bounds (panic) at cwt.rs:613")
+    if not one_int:
+        raise NotImplementedError("two-integral icwt (cwt.rs:629-712) is not restated")
+    dj = math.log(scales[1] / scales[0]) if (n_scales > 1 and scales[1] > scales[0]) else 0.1  # :595-599
+    final_norm = (2.0 / adm) * dj
+    norm = np.ones(n_scales) if l1_norm else 1.0 / np.sqrt(scales[:n_scales])                 # :606-610
+    x = np.zeros(x_length)
+    for i in range(n_scales):                                                                  # :620-623 (i ascending)
+        x += Wx[i, :x_length].real * norm[i]
+    return x * final_norm + x_mean                                                             # :624

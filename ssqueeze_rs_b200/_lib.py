@@ -56,6 +56,8 @@ SIGNATURES = {
     "ssq_cwt_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_dbl, c_int, c_u32, c_vp, c_vp]),
     "ssq_ssq_cwt_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_dbl, c_int, c_int, c_int, c_int,
                                 c_dbl, c_u32, c_vp, c_vp]),
+    "ssq_icwt_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_i64, c_dbl, c_u32, c_vp]),
+    "ssq_icwt_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_int, c_i64, c_dbl, c_u32, c_vp]),
     "ssq_ssq_stft_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl,
                                        c_int, c_int, c_dbl, c_u32, c_vp]),
     "ssq_stft_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),

@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import (FLAG_L2_NORM, FLAG_MODULATED, FLAG_NO_FLIPUD, FLAG_RPADDED, FLAG_SIMD_SCALES, PAD, SQUEEZE,
                    default_context, load, raise_status)
 
-__all__ = ["hello_from_bin", "stft", "ssq_stft", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt"]
+__all__ = ["hello_from_bin", "stft", "ssq_stft", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt", "icwt"]
 
 
 def _f64_1d(a, name):
@@ -230,3 +230,25 @@ def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=3
                                 0 if flipud else FLAG_NO_FLIPUD, _ptr(Tx), _ptr(sf))
     raise_status(st, ctx.handle)
     return Tx, sf
+
+
+def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_mean=0.0, padtype="reflect",
+         rpadded=False, l1_norm=True):
+    """cwt.rs:548-566 (declared in src/ssqueeze/_rs.pyi:62-73, never registered by lib.rs:25-32).
+    One-integral reconstruction; `nv`, `padtype`, `rpadded` are accepted and unused as in the reference."""
+    if not isinstance(Wx, np.ndarray) or Wx.ndim != 2 or Wx.dtype != np.complex128:
+        raise TypeError("argument 'Wx': expected a 2-D numpy.ndarray of complex128")
+    if scales is None:
+        raise ValueError("Scales must be provided")  # cwt.rs:572-575
+    sc = _f64_1d(scales, "scales")
+    Wx = np.ascontiguousarray(Wx)
+    ns, ncols = Wx.shape
+    if len(sc) < ns:
+        raise _lib.PanicException("scales shorter than Wx.shape[0]: index out of bounds at cwt.rs:604")
+    xl = ncols if x_len is None else int(x_len)
+    x = np.empty(max(xl, 0), dtype=np.float64)
+    ctx = default_context()
+    st = load().ssq_icwt_f64(ctx.handle, _ptr(Wx), ns, ncols, 1 if _str(wavelet, "wavelet") == "morlet" else 0,
+                             _ptr(sc), 1 if one_int else 0, xl, float(x_mean), 0 if l1_norm else FLAG_L2_NORM, _ptr(x))
+    raise_status(st, ctx.handle)
+    return x

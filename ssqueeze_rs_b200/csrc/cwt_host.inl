@@ -428,3 +428,55 @@ extern "C" ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, 
                                 padtype, squeezing, maprange, gamma, flags, (float*)ctx->ws_out.p, ssq_freqs));
   return download_f32_as_f64(ctx, ctx->ws_out.p, cnt * 2, Tx);
 }
+
+// icwt: cwt.rs:548-718, one-integral branch only.
+extern "C" ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_t channels, int64_t ns, int64_t n_cols,
+                                         int wavelet, const double* scales, int one_int, int64_t x_len, double x_mean,
+                                         unsigned flags, float* d_x) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!d_Wx || !d_x) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  if (!scales) return ssq_fail(ctx, SSQ_EINVAL, "Scales must be provided");  // cwt.rs:572-575
+  if (channels < 1 || ns < 1 || n_cols < 1) return ssq_fail(ctx, SSQ_EINVAL, "icwt: empty Wx");
+  if (x_len <= 0) x_len = n_cols;
+  if (x_len > n_cols)
+    return ssq_fail(ctx, SSQ_EPANIC, "x_len %lld > Wx.shape[1] %lld: index out of bounds in the reference (cwt.rs:613)",
+                    (long long)x_len, (long long)n_cols);
+  if (!one_int)
+    return ssq_fail(ctx, SSQ_EUNSUPPORTED, "icwt: the two-integral branch (cwt.rs:629-712) is not built; use one_int=True");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const double adm = wavelet == SSQ_WAVELET_MORLET ? 0.776 : 1.0;                                   // cwt.rs:579-583
+  const double dj = (ns > 1 && scales[1] > scales[0]) ? std::log(scales[1] / scales[0]) : 0.1;     // :595-599
+  const double final_norm = (2.0 / adm) * dj;
+  std::vector<float> hn((size_t)ns);
+  for (int64_t i = 0; i < ns; ++i)
+    hn[(size_t)i] = (flags & SSQ_FLAG_L2_NORM) ? (float)(1.0 / std::sqrt(scales[i])) : 1.f;       // :606-610
+  SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, hn.size() * sizeof(float)));
+  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, hn.data(), hn.size() * sizeof(float), cudaMemcpyHostToDevice));
+  dim3 g((unsigned)((x_len + 255) / 256), (unsigned)channels);
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  icwt_kernel<<<g, 256, 0, ctx->stream>>>((const float2*)d_Wx, ns, n_cols, x_len, (const float*)ctx->cwt_scales.p,
+                                          (float)final_norm, (float)x_mean, d_x);
+  SSQ_TRY(ssq_check_launch(ctx, "icwt_kernel"));
+  ctx->last_kernel = "icwt_kernel";
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_icwt_f64(ssq_ctx* ctx, const double* Wx, int64_t ns, int64_t n_cols, int wavelet,
+                                   const double* scales, int one_int, int64_t x_len, double x_mean, unsigned flags,
+                                   double* x) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!Wx || !x) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  if (!scales) return ssq_fail(ctx, SSQ_EINVAL, "Scales must be provided");
+  if (ns < 1 || n_cols < 1) return ssq_fail(ctx, SSQ_EINVAL, "icwt: empty Wx");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (x_len <= 0) x_len = n_cols;
+  const size_t cnt = (size_t)ns * n_cols;
+  SSQ_TRY(upload_f64_as_f32(ctx, Wx, cnt * 2, ctx->ws_in));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, (size_t)std::max<int64_t>(x_len, 1) * sizeof(float)));
+  SSQ_TRY(ssq_icwt_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, ns, n_cols, wavelet, scales, one_int, x_len, x_mean,
+                             flags, (float*)ctx->ws_out.p));
+  return download_f32_as_f64(ctx, ctx->ws_out.p, (size_t)x_len, x);
+}

@@ -394,3 +394,18 @@ __global__ void ssq_cwt_reassign_kernel(const SsqCwtParams P) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------
+// icwt, one-integral branch (cwt.rs:590-627): x[c][j] = final_norm * sum_i Re Wx[c][i][j] * norm_i + x_mean,
+// scales ascending in i as the reference sums them; coalesced along j.
+// ------------------------------------------------------------------------------------
+__global__ void icwt_kernel(const float2* __restrict__ Wx, int64_t ns, int64_t n_cols, int64_t x_len,
+                            const float* __restrict__ norm, float final_norm, float x_mean, float* __restrict__ x) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (j >= x_len) return;
+  const float2* w = Wx + (size_t)c * ns * n_cols + j;
+  float s = 0.f;
+  for (int64_t i = 0; i < ns; ++i) s = fmaf(w[(size_t)i * n_cols].x, __ldg(norm + i), s);
+  x[(size_t)c * x_len + j] = fmaf(s, final_norm, x_mean);
+}

@@ -20,7 +20,7 @@ static const double kEps64 = 2.2204460492503131e-16;
 // library / context
 // ===========================================================================
 extern "C" const char* ssq_version(void) {
-  return "ssqcuda 0.1 (B200 sm_100a; stft, ssq_stft, istft, issq_stft, cwt, cwt_simd, ssq_cwt)";
+  return "ssqcuda 0.2 (B200 sm_100a; stft, ssq_stft, istft, issq_stft, cwt, cwt_simd, ssq_cwt, icwt, ssq_stft streaming)";
 }
 
 extern "C" int ssq_device_count(void) {

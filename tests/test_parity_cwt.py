@@ -184,3 +184,29 @@ def test_cwt_fft_plans(N):
     Wx, _, _ = rs.cwt(x, "gmw", sc, fs=1000.0, rpadded=True, padtype="zero")
     Wo, _, _ = O.cwt(x, "gmw", sc, fs=1000.0, rpadded=True, padtype="zero")
     assert rel(Wx, Wo) < RTOL
+
+
+def test_icwt_one_integral():
+    """cwt.rs:548-627 (one-integral branch) against the oracle, both norms, x_len, x_mean."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import PanicException, SsqError
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(3000)
+    sc = 2.0 ** np.linspace(1, 8, 40)
+    for wav in ("gmw", "morlet"):
+        for l1 in (True, False):
+            Wx, _, _ = rs.cwt(x, wav, sc, fs=1.0, l1_norm=l1)
+            xr = rs.icwt(Wx, wav, sc, l1_norm=l1, x_mean=0.25)
+            xo = O.icwt(Wx, wav, sc, l1_norm=l1, x_mean=0.25)
+            assert xr.shape == (3000,) and xr.dtype == np.float64
+            assert np.abs(xr - xo).max() < RTOL * np.abs(xo).max()
+    Wx, _, _ = rs.cwt(x, "gmw", sc, fs=1.0)
+    xo = O.icwt(Wx, "gmw", sc, x_len=1000)
+    xr = rs.icwt(Wx, "gmw", sc, x_len=1000)
+    assert len(xr) == 1000 and np.abs(xr - xo).max() < RTOL * np.abs(xo).max()
+    with pytest.raises(ValueError):
+        rs.icwt(Wx)                                   # "Scales must be provided"
+    with pytest.raises(PanicException):
+        rs.icwt(Wx, "gmw", sc, x_len=5000)            # index out of bounds in the reference
+    with pytest.raises(SsqError):
+        rs.icwt(Wx, "gmw", sc, one_int=False)         # two-integral branch not built
