@@ -236,9 +236,16 @@ static ssq_status plan_generic_tiles(ssq_ctx* ctx, int n_fft, int n_freqs, int64
   const int acc_stride = n_freqs | 1;
   int F = 32, nw = 8;
   auto need = [&](int F_, int nw_) {
-    return ((size_t)F_ * acc_stride + (size_t)nw_ * 2 * n_fft + (size_t)n_fft) * sizeof(float2);
+    return ((size_t)F_ * acc_stride + (size_t)nw_ * 2 * n_fft + (size_t)n_fft) * sizeof(float2) +
+           (size_t)nw_ * ((n_freqs + 7) & ~7);  // + per-warp tag bytes (stft_generic_kernel)
   };
-  while (nw > 1 && need(F, nw) > budget) nw >>= 1;
+  // keep the warps first (they are what hides latency), then the frames per tile (row segments of
+  // F * 8 B); shrink F down to the warp count before giving up warps
+  while (F > nw && need(F, nw) > budget) F >>= 1;
+  while (nw > 1 && need(F, nw) > budget) {
+    nw >>= 1;
+    F = std::max(F >> 1, 1);
+  }
   while (F > 1 && need(F, nw) > budget) F >>= 1;
   if (need(F, nw) > budget)
     return ssq_fail(ctx, SSQ_EUNSUPPORTED, "n_fft=%d needs %zu B of shared memory per CTA (> %zu)", n_fft,

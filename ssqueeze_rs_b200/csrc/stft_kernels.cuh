@@ -126,7 +126,7 @@ __device__ __forceinline__ float2* warp_fft_generic(float2* A, float2* B, const 
 // ------------------------------------------------------------------------
 // Generic kernel: any n_fft >= 2 (radix-4/2 Stockham for powers of two, direct
 // DFT otherwise), warp per frame, everything staged in shared memory.
-// Dynamic smem: acc[F*acc_stride] | per-warp work[2*n_fft] | tw[n_fft].
+// Dynamic smem: acc[F*acc_stride] | per-warp work[2*n_fft] | tw[n_fft] | per-warp tags[n_freqs].
 // ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
   extern __shared__ float2 smem[];
@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
   float2* acc = smem;
   float2* work = acc + (size_t)P.F * P.acc_stride + (size_t)warp * 2 * N;
   float2* twid = acc + (size_t)P.F * P.acc_stride + (size_t)nw * 2 * N;
+  // per-warp destination-bin tags (n_freqs bytes, rounded up to 8) behind the twiddles
+  unsigned char* tag = reinterpret_cast<unsigned char*>(twid + N) + (size_t)warp * ((P.n_freqs + 7) & ~7);
   for (int i = threadIdx.x; i < N; i += blockDim.x) twid[i] = P.tw[i];
 
   for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -158,34 +160,59 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
       __syncwarp();
       float2* Z = warp_fft_generic(A, B, twid, N, P.log2n, P.is_pow2, lane);
 
-      // split + phase transform + reassignment for bins k = lane, lane+32, ...
+      // split + phase transform + reassignment.  Lane owns the S consecutive bins lane*S .. lane*S+S-1
+      // (S odd: conflict-free strided reads of Z), so the 32 sources of a step are S bins apart and
+      // rarely share a destination; a byte tag per destination bin detects the cases that do (fp32
+      // shared atomics are CAS loops on sm_100a), which are then serialised in ascending source order.
       float2* col = acc + (size_t)fl * P.acc_stride;
-      for (int k = lane; k < P.n_freqs; k += 32) {
-        const float2 zk = Z[k];
-        const float2 zn = Z[k == 0 ? 0 : N - k];
-        float c = zk.x + zn.x, d = zk.y - zn.y;  // 2*Sx
-        float a = zk.y + zn.y, b = zn.x - zk.x;  // 2*V
-        if (P.modulated) {
-          // multiply by exp(+2 pi i k (N/2)/N) = conj(tw[(k*(N/2)) mod N])
-          const int m = (int)(((int64_t)k * (N / 2)) % N);
-          const float2 t = twid[m];
-          float2 s2 = make_float2(c * t.x + d * t.y, d * t.x - c * t.y);
-          float2 v2 = make_float2(a * t.x + b * t.y, b * t.x - a * t.y);
-          c = s2.x; d = s2.y; a = v2.x; b = v2.y;
+      const int S = ((P.n_freqs + 31) >> 5) | 1;
+      for (int i = 0; i < S; ++i) {
+        const int k = lane * S + i;
+        const bool valid = k < P.n_freqs;
+        int kb = -1;
+        float vre = 0.f, vim = 0.f;
+        if (valid) {
+          const float2 zk = Z[k];
+          const float2 zn = Z[k == 0 ? 0 : N - k];
+          float c = zk.x + zn.x, d = zk.y - zn.y;  // 2*Sx
+          float a = zk.y + zn.y, b = zn.x - zk.x;  // 2*V
+          if (P.modulated) {
+            // multiply by exp(+2 pi i k (N/2)/N) = conj(tw[(k*(N/2)) mod N])
+            const int m = (int)(((int64_t)k * (N / 2)) % N);
+            const float2 t = twid[m];
+            float2 s2 = make_float2(c * t.x + d * t.y, d * t.x - c * t.y);
+            float2 v2 = make_float2(a * t.x + b * t.y, b * t.x - a * t.y);
+            c = s2.x; d = s2.y; a = v2.x; b = v2.y;
+          }
+          const float den = c * c + d * d;
+          const bool gated = den < P.gate2;  // |Sx| < gamma (ssq_stft.rs:23)
+          const float binf = fabsf((float)k - (b * c - a * d) / den * P.cphase);
+          const size_t oidx = ((size_t)ch * P.n_freqs + k) * P.n_frames + frame;
+          if (P.aux_Sx) P.aux_Sx[oidx] = make_float2(0.5f * c, 0.5f * d);
+          if (P.aux_dSx) P.aux_dSx[oidx] = make_float2(a * P.dsx_scale, b * P.dsx_scale);
+          if (P.aux_w) P.aux_w[oidx] = gated ? __int_as_float(0x7f800000) : binf * P.dw_f;
+          if (P.mode == 1) {
+            col[k] = make_float2(0.5f * c, 0.5f * d);
+          } else if (!gated) {
+            kb = ssq_bin_from(binf, P.n_freqs);
+            if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) vre = P.leb_val;
+            else { vre = c * P.tx_scale; vim = d * P.tx_scale; }
+          }
         }
-        const float den = c * c + d * d;
-        const bool gated = den < P.gate2;  // |Sx| < gamma (ssq_stft.rs:23)
-        const float binf = fabsf((float)k - (b * c - a * d) / den * P.cphase);
-        const size_t oidx = ((size_t)ch * P.n_freqs + k) * P.n_frames + frame;
-        if (P.aux_Sx) P.aux_Sx[oidx] = make_float2(0.5f * c, 0.5f * d);
-        if (P.aux_dSx) P.aux_dSx[oidx] = make_float2(a * P.dsx_scale, b * P.dsx_scale);
-        if (P.aux_w) P.aux_w[oidx] = gated ? __int_as_float(0x7f800000) : binf * P.dw_f;
-        if (P.mode == 1) {
-          col[k] = make_float2(0.5f * c, 0.5f * d);
-        } else if (!gated) {
-          const int kb = ssq_bin_from(binf, P.n_freqs);
-          if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) smem_add_f2(&col[kb], P.leb_val, 0.f);
-          else smem_add_f2(&col[kb], c * P.tx_scale, d * P.tx_scale);
+        if (P.mode == 0) {
+          const bool on = kb >= 0;
+          if (on) tag[kb] = (unsigned char)lane;
+          __syncwarp();
+          const bool mine = !on || tag[kb] == (unsigned char)lane;
+          if (__all_sync(0xffffffffu, mine)) {
+            if (on) { float2 t = col[kb]; t.x += vre; t.y += vim; col[kb] = t; }
+          } else {
+            for (int src = 0; src < 32; ++src) {  // rare: ascending lane = ascending source bin
+              if (lane == src && on) { float2 t = col[kb]; t.x += vre; t.y += vim; col[kb] = t; }
+              __syncwarp();
+            }
+          }
+          __syncwarp();
         }
       }
       __syncwarp();
