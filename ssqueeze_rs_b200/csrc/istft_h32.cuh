@@ -1,4 +1,5 @@
-// istft_h32.cuh -- inverse STFT for n_fft = 512, hop = 32 (BASELINE.json configs[3]).
+// istft_h32.cuh -- inverse STFT for n_fft = 512 (BASELINE.json configs[3]: hop = 32; the tile kernel
+// that is launched takes any hop).
 //
 // old/ssqueezepy/_stft.py:184-256 in the Rust framing (unmodulated, unpad at
 // (n_fft-1)/2).  A warp owns a RUN of consecutive frames of one channel:
@@ -30,6 +31,7 @@ struct Istft32Params {
   float* xacc;       // [channels, L] zero-initialised
   int run;           // frames per run (multiple of 4)
   int64_t runs_per_channel, total_runs;
+  int hop;           // tile kernel: any hop >= 1 (the per-warp-run kernel needs hop == 32)
 };
 
 // 8-byte asynchronous global->shared copy.  A warp fetches 32 B row segments, so the four
@@ -284,16 +286,17 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const 
     __syncthreads();
     // ---- overlap-add gather over the tile span, one red per padded sample ---------------------------
     {
-      const int span = (nf - 1) * 32 + N;
-      float* xo = P.xacc + (size_t)ch * P.L + f0 * 32;
-      const int64_t room = P.L - f0 * 32;
+      const int hop = P.hop;
+      const int span = (nf - 1) * hop + N;
+      float* xo = P.xacc + (size_t)ch * P.L + f0 * hop;
+      const int64_t room = P.L - f0 * hop;
       const float* Sf = reinterpret_cast<const float*>(S);
       for (int p = threadIdx.x; p < span; p += blockDim.x) {
-        const int fhi = min(nf - 1, p >> 5);
-        const int flo = max(0, (p - N + 32) >> 5);
+        const int fhi = min(nf - 1, p / hop);
+        const int flo = p < N ? 0 : (p - N + hop) / hop;  // ceil((p - N + 1) / hop)
         float acc = 0.f;
-        for (int f = flo; f <= fhi; ++f) acc += Sf[f * (2 * AS) + (p - 32 * f)];
-        if (p < room) atomicAdd(xo + p, acc);
+        for (int f = flo; f <= fhi; ++f) acc += Sf[f * (2 * AS) + (p - hop * f)];
+        if (p < room && flo <= fhi) atomicAdd(xo + p, acc);
       }
     }
     __syncthreads();

@@ -452,7 +452,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
   SSQ_TRY(devbuf_reserve(ctx, ctx->ws_misc, (size_t)channels * L * sizeof(float)));
   SSQ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_misc.p, 0, (size_t)channels * L * sizeof(float), ctx->stream));
 
-  if (n_fft == 512 && hop == 32 && !getenv("SSQ_NO_H32")) {
+  if (n_fft == 512 && !getenv("SSQ_NO_H32") && (hop == 32 || !getenv("SSQ_ISTFT_RUNS"))) {
     Istft32Params Q;
     memset(&Q, 0, sizeof(Q));
     Q.Sx = (const float2*)d_Sx;
@@ -463,6 +463,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
     Q.wa = T.wa;
     Q.tw = T.tw;
     Q.xacc = (float*)ctx->ws_misc.p;
+    Q.hop = hop;
     SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (getenv("SSQ_ISTFT_RUNS")) {  // per-warp runs with register overlap-add (kept for comparison)
       int run = 32;

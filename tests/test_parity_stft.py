@@ -453,3 +453,20 @@ def test_channel_sharder_matches_engine():
     for devs in ([0], [0, 0], [0, 0, 0]):
         out = ChannelSharder(devs).ssq_stft(x, win, 512, 32, 30000.0)
         assert out.shape == ref.shape and np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("hop,N", [(1, 900), (17, 5000), (64, 9000), (128, 20000), (256, 7000), (600, 10000)])
+def test_istft_512_any_hop(hop, N):
+    """The n_fft=512 tile kernel at hops other than 32 (gather overlap-add with a runtime hop)."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    rng = np.random.default_rng(hop)
+    x = rng.standard_normal(N)
+    win = np.hanning(514)[1:-1].copy()
+    So, _ = O.stft(x, 512, hop, win, "reflect")
+    So = So * (1 + 0.05 * rng.standard_normal(So.shape))
+    for wexp in (1, 0):
+        xr = rs.istft(So, win, n_fft=512, hop_len=hop, N=N, win_exp=wexp)
+        assert "istft512_tile" in _lib.default_context().last_kernel_name()
+        xo = O.istft(So, win, n_fft=512, hop_len=hop, N=N, win_exp=wexp)
+        assert np.abs(xr - xo).max() < RTOL * max(np.abs(xo).max(), 1e-30), (hop, wexp)
