@@ -94,6 +94,18 @@ def load():
         if _lib is not None:
             return _lib
         path = lib_path()
+        if not os.path.exists(path) and "SSQCUDA_LIB" not in os.environ:
+            # a fresh checkout (the .so is not tracked): compile it in-tree once if nvcc is around;
+            # this is a build step, not a fallback -- without the library every call still fails
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location(
+                    "__graft_entry__", os.path.join(os.path.dirname(_HERE), "__graft_entry__.py"))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                mod.build_cuda()
+            except Exception:
+                pass
         if not os.path.exists(path):
             raise ImportError(
                 f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
