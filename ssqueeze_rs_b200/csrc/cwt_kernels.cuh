@@ -271,11 +271,43 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   const bool inv = P.sign > 0;
 
   float2 v[16];
+  if (P.load_mode == 2) {
+    // x-hat * psi-hat generated on the fly: the row's constants once per thread, and an exact integer
+    // early-out -- psihat() returns 0 beyond its cut-off, i.e. for spectrum indices >= blim
+    const int64_t gr = P.row0 + row;
+    const int which = (int)(gr % P.nd);
+    const int64_t cs = gr / P.nd;
+    const float scale = __ldg(P.scales + (int)(cs % P.ns));
+    const float2* xh = P.xhat + (size_t)(cs / P.ns) * L;
+    const float cut = P.wavelet == SSQ_WAVELET_MORLET ? 14.5f : 4.5f;
+    int64_t blim = (L >> 1) + 1;  // negative frequencies: psi-hat = 0 (cwt.rs:496-541)
+    if (scale > 0.f) blim = min(blim, (int64_t)(cut * (float)L / (6.283185307179586f * scale) * 1.0001f) + 2);
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    float2 x = pass_load(P, row, j + (int64_t)(g + 8 * u) * Q);
-    if (inv) x.y = -x.y;
-    v[u] = x;
+    for (int u = 0; u < 16; ++u) {
+      const int64_t idx = (j + (int64_t)(g + 8 * u) * Q) >> P.up_shift;
+      float2 x = make_float2(0.f, 0.f);
+      if (idx < blim) {
+        const float xi = 6.283185307179586f * (float)idx / (float)L;  // wavelets/base.rs:18-33, idx <= L/2
+        const float ps = psihat(P.wavelet, scale * xi);
+        if (ps != 0.f) {
+          const float2 h = __ldg(xh + idx);
+          x = make_float2(h.x * ps, h.y * ps);
+          if (which == 1) {  // * i*xi/dt (cwt.rs:205-209, ssq_cwt.rs:374-377)
+            const float f = xi * P.inv_dt;
+            x = make_float2(-x.y * f, x.x * f);
+          }
+        }
+      }
+      if (inv) x.y = -x.y;
+      v[u] = x;
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      float2 x = pass_load(P, row, j + (int64_t)(g + 8 * u) * Q);
+      if (inv) x.y = -x.y;
+      v[u] = x;
+    }
   }
   if (P.log2Ns > 0) {
     // inter-pass twiddle W^{kk (g + 8u)} = W^{kk g} (W^{8 kk})^u: two table look-ups, then powers by
@@ -320,6 +352,23 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
       b[k2].y = -b[k2].y;
     }
   }
+  // store functor with the row's constants hoisted (the per-element version divides 64-bit indices)
+  float2* sdst = P.out + (size_t)row * L;
+  float sscale = 1.f;
+  int64_t soff = 0, scols = L;
+  if (P.store_mode == 1) {
+    const int64_t gr = P.row0 + row;
+    const int64_t cs = gr / P.nd;  // channel * ns + scale
+    sdst = ((gr % P.nd) ? P.outD : P.outW) + (size_t)cs * P.out_cols;
+    sscale = P.out_scale;
+    if (P.l2_norm) sscale *= sqrtf(__ldg(P.scales + (int)(cs % P.ns)));  // cwt.rs:253
+    soff = P.n1;
+    scols = P.out_cols;
+  }
+  auto store = [&](int64_t o, float2 val) {
+    const int64_t col = o - soff;
+    if (col >= 0 && col < scols) sdst[col] = make_float2(val.x * sscale, val.y * sscale);
+  };
   if (P.log2Ns == 0) {
     // out index = j * 128 + k: transpose so that the CTA writes its 4096 outputs contiguously
     __syncthreads();
@@ -332,14 +381,14 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int e = threadIdx.x + 8 * TC * i;
-      pass_store(P, row, (j0 << 7) + e, buf[(e >> 7) * 129 + (e & 127)]);
+      store((j0 << 7) + e, buf[(e >> 7) * 129 + (e & 127)]);
     }
   } else {
     const int64_t base = ((j - kk) << 7) + kk;
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
-      pass_store(P, row, base + (int64_t)(g + 16 * k2) * Ns, a[k2]);
-      pass_store(P, row, base + (int64_t)(g + 8 + 16 * k2) * Ns, b[k2]);
+      store(base + (int64_t)(g + 16 * k2) * Ns, a[k2]);
+      store(base + (int64_t)(g + 8 + 16 * k2) * Ns, b[k2]);
     }
   }
 }
