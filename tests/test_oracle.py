@@ -105,3 +105,22 @@ def test_error_behaviour():
         O.ssq_stft(x, np.ones(16), n_fft=8)  # win_len > n_fft (ssq_stft.rs:96-101)
     with pytest.raises(ValueError):
         O.cwt(x, t=np.array([0.0]))  # cwt.rs:68-70
+
+
+def test_oracle_icwt_formula_and_errors():
+    """cwt.rs:548-627 (one-integral icwt): constants, norms, x_len / x_mean handling."""
+    rng = np.random.default_rng(0)
+    Wx = rng.standard_normal((6, 50)) + 1j * rng.standard_normal((6, 50))
+    sc = 2.0 ** np.arange(1, 7, dtype=np.float64)
+    x = O.icwt(Wx, "gmw", sc, x_mean=0.5)
+    assert np.allclose(x, 2.0 * np.log(2.0) * Wx.real.sum(0) + 0.5, rtol=1e-14)          # adm = 1, dj = ln 2
+    xm = O.icwt(Wx, "morlet", sc)
+    assert np.allclose(xm, (2.0 / 0.776) * np.log(2.0) * Wx.real.sum(0), rtol=1e-14)     # adm = 0.776
+    x2 = O.icwt(Wx, "gmw", sc, l1_norm=False, x_len=20)
+    assert x2.shape == (20,)
+    assert np.allclose(x2, 2.0 * np.log(2.0) * (Wx.real[:, :20] / np.sqrt(sc)[:, None]).sum(0), rtol=1e-14)
+    assert np.allclose(O.icwt(Wx, "gmw", sc[::-1].copy()), 2.0 * 0.1 * Wx.real.sum(0), rtol=1e-14)  # dj default 0.1
+    with pytest.raises(ValueError):
+        O.icwt(Wx)
+    with pytest.raises(IndexError):
+        O.icwt(Wx, "gmw", sc, x_len=51)
