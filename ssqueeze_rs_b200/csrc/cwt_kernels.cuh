@@ -261,12 +261,14 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   __shared__ float2 w128[128];  // W_128^m
   const int c = threadIdx.x % TC, g = threadIdx.x / TC;
   if (threadIdx.x < 128) w128[threadIdx.x] = tw_fwd(P, (int64_t)threadIdx.x << (P.log2L - 7));
-  const int64_t L = (int64_t)1 << P.log2L;
-  const int64_t Q = L >> 7;
-  const int64_t Ns = (int64_t)1 << P.log2Ns;
+  // in-row indices are 32-bit (L <= 2^27, checked on the host): the passes are issue-bound and 64-bit
+  // index arithmetic was a fifth of their instructions
+  const int L = 1 << P.log2L;
+  const int Q = L >> 7;
+  const int Ns = 1 << P.log2Ns;
   const int row = blockIdx.y;
-  const int64_t j0 = (int64_t)blockIdx.x * TC, j = j0 + c;
-  const int64_t kk = j & (Ns - 1);
+  const int j0 = blockIdx.x * TC, j = j0 + c;
+  const int kk = j & (Ns - 1);
   const int twshift = P.log2L - P.log2Ns - 7;  // W_{128 Ns}^e = W_L^(e << twshift)
   const bool inv = P.sign > 0;
 
@@ -280,11 +282,11 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
     const float scale = __ldg(P.scales + (int)(cs % P.ns));
     const float2* xh = P.xhat + (size_t)(cs / P.ns) * L;
     const float cut = P.wavelet == SSQ_WAVELET_MORLET ? 14.5f : 4.5f;
-    int64_t blim = (L >> 1) + 1;  // negative frequencies: psi-hat = 0 (cwt.rs:496-541)
-    if (scale > 0.f) blim = min(blim, (int64_t)(cut * (float)L / (6.283185307179586f * scale) * 1.0001f) + 2);
+    int blim = (L >> 1) + 1;  // negative frequencies: psi-hat = 0 (cwt.rs:496-541)
+    if (scale > 0.f) blim = (int)fminf((float)blim, cut * (float)L / (6.283185307179586f * scale) * 1.0001f + 2.f);
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      const int64_t idx = (j + (int64_t)(g + 8 * u) * Q) >> P.up_shift;
+      const int idx = (j + (g + 8 * u) * Q) >> P.up_shift;
       float2 x = make_float2(0.f, 0.f);
       if (idx < blim) {
         const float xi = 6.283185307179586f * (float)idx / (float)L;  // wavelets/base.rs:18-33, idx <= L/2
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   } else {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      float2 x = pass_load(P, row, j + (int64_t)(g + 8 * u) * Q);
+      float2 x = pass_load(P, row, j + (g + 8 * u) * Q);
       if (inv) x.y = -x.y;
       v[u] = x;
     }
@@ -312,9 +314,9 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   if (P.log2Ns > 0) {
     // inter-pass twiddle W^{kk (g + 8u)} = W^{kk g} (W^{8 kk})^u: two table look-ups, then powers by
     // repeated squaring / short products (every power is at most 4 multiplications deep)
-    const float2 wg = tw_fwd(P, (kk * g) << twshift);
+    const float2 wg = tw_fwd(P, (int64_t)((kk * g) << twshift));
     float2 p[16];
-    p[1] = tw_fwd(P, (kk * 8) << twshift);
+    p[1] = tw_fwd(P, (int64_t)((kk * 8) << twshift));
     p[2] = cmulf(p[1], p[1]);
     p[4] = cmulf(p[2], p[2]);
     p[8] = cmulf(p[4], p[4]);
@@ -355,18 +357,18 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   // store functor with the row's constants hoisted (the per-element version divides 64-bit indices)
   float2* sdst = P.out + (size_t)row * L;
   float sscale = 1.f;
-  int64_t soff = 0, scols = L;
+  int soff = 0, scols = L;
   if (P.store_mode == 1) {
     const int64_t gr = P.row0 + row;
     const int64_t cs = gr / P.nd;  // channel * ns + scale
     sdst = ((gr % P.nd) ? P.outD : P.outW) + (size_t)cs * P.out_cols;
     sscale = P.out_scale;
     if (P.l2_norm) sscale *= sqrtf(__ldg(P.scales + (int)(cs % P.ns)));  // cwt.rs:253
-    soff = P.n1;
-    scols = P.out_cols;
+    soff = (int)P.n1;
+    scols = (int)P.out_cols;
   }
-  auto store = [&](int64_t o, float2 val) {
-    const int64_t col = o - soff;
+  auto store = [&](int o, float2 val) {
+    const int col = o - soff;
     if (col >= 0 && col < scols) sdst[col] = make_float2(val.x * sscale, val.y * sscale);
   };
   if (P.log2Ns == 0) {
@@ -384,11 +386,11 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
       store((j0 << 7) + e, buf[(e >> 7) * 129 + (e & 127)]);
     }
   } else {
-    const int64_t base = ((j - kk) << 7) + kk;
+    const int base = ((j - kk) << 7) + kk;
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
-      store(base + (int64_t)(g + 16 * k2) * Ns, a[k2]);
-      store(base + (int64_t)(g + 8 + 16 * k2) * Ns, b[k2]);
+      store(base + (g + 16 * k2) * Ns, a[k2]);
+      store(base + (g + 8 + 16 * k2) * Ns, b[k2]);
     }
   }
 }
