@@ -221,9 +221,11 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
   int nfr = 0;
   bool inner = false;
   float xw[16];
-  auto open_tile = [&](int64_t tile) {  // single call site (see the loop): sets the warp's frames, loads frame f0's window
-    const int ch = (int)(tile / P.tiles_per_channel);
-    f0 = (tile % P.tiles_per_channel) * F + 4 * warp;
+  // tile indices are 32-bit (checked by the launcher): 64-bit divisions cost ~100 instructions each
+  const int tpc = (int)P.tiles_per_channel, ntiles = (int)P.total_tiles;
+  auto open_tile = [&](int tile) {  // single call site (see the loop): sets the warp's frames, loads frame f0's window
+    const int ch = tile / tpc;
+    f0 = (int64_t)(tile - ch * tpc) * F + 4 * warp;
     nfr = (int)max((int64_t)0, min((int64_t)4, P.n_frames - f0));
     f0 += P.frame0;  // from here on f0 is the GLOBAL frame index (sample addressing only)
     xc = P.x + (size_t)ch * P.x_stride;
@@ -243,12 +245,12 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
 
   // The loop starts one (virtual) tile early so that open_tile is inlined exactly once: the first
   // pass only fetches the window of the CTA's first real tile.
-  for (int64_t tile = (int64_t)blockIdx.x - gridDim.x; tile < P.total_tiles; tile += gridDim.x) {
+  for (int tile = (int)blockIdx.x - (int)gridDim.x; tile < ntiles; tile += (int)gridDim.x) {
     const bool real = tile >= 0;
-    const int tch = real ? (int)(tile / P.tiles_per_channel) : 0;
-    const int64_t tf0 = real ? (tile % P.tiles_per_channel) * F : 0;
+    const int tch = real ? tile / tpc : 0;
+    const int64_t tf0 = real ? (int64_t)(tile - tch * tpc) * F : 0;
     const int tnf = real ? (int)min((int64_t)F, P.n_frames - tf0) : 0;
-    const int64_t next = tile + gridDim.x;
+    const int next = tile + (int)gridDim.x;
     const int my_n = real ? nfr : 0;
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
         }
       }
       if (s == 3) {
-        if (next < P.total_tiles) open_tile(next);
+        if (next < ntiles) open_tile(next);
       } else if (s + 1 < my_n) {
         if (SLIDE) {
 #pragma unroll
@@ -315,12 +317,14 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
 }
 
 template <int NW>
-static ssq_status stft_h32r_launch_nw(ssq_ctx* ctx, StftParams& P) {
+static ssq_status stft_h32r_launch_nw(ssq_ctx* ctx, StftParams& P, bool* done) {
   constexpr int F = 4 * NW;
   P.F = F;
   P.acc_stride = H32R_AS;
   P.tiles_per_channel = (P.n_frames + F - 1) / F;
   P.total_tiles = P.tiles_per_channel * P.channels;
+  if (P.total_tiles > (int64_t)0x7ff00000) return SSQ_OK;  // *done stays false: the older kernels index in 64 bits
+  *done = true;
   const size_t smem = ((size_t)512 + 72 + (size_t)F * H32R_AS + (size_t)NW * 512) * sizeof(float2);
   const int grid = (int)std::min<int64_t>(P.total_tiles, (int64_t)ctx->num_sms * (16 / NW));
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
@@ -346,8 +350,7 @@ static ssq_status stft_h32r_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   if (P.n_fft != 512 || P.modulated || getenv("SSQ_NO_H32R")) return SSQ_OK;
   if (P.hop != 32 && getenv("SSQ_H32R_HOP32_ONLY")) return SSQ_OK;
   static const int nw_env = getenv("SSQ_H32R_NW") ? atoi(getenv("SSQ_H32R_NW")) : 4;
-  if (nw_env == 4) SSQ_TRY(stft_h32r_launch_nw<4>(ctx, P));
-  else SSQ_TRY(stft_h32r_launch_nw<8>(ctx, P));
-  *done = true;
+  if (nw_env == 4) SSQ_TRY(stft_h32r_launch_nw<4>(ctx, P, done));
+  else SSQ_TRY(stft_h32r_launch_nw<8>(ctx, P, done));
   return SSQ_OK;
 }
