@@ -33,14 +33,21 @@ struct H32RItem {
 };
 
 // Pair (A, B) = (Z[k_a], Z[512 - k_a]) -> item of source bin |skf|.  sign(skf) < 0: roles swapped.
+// colB != nullptr (stft, hop 32): the FFT carried TWO frames, z = x_A w + i x_B w; the "V" half of the
+// split is then the second frame's spectrum and goes to its own column.
 template <int MODE, int SQZ>
-__device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float2* col, float skf, float2 A, float2 B) {
+__device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float2* col, float2* colB, float skf, float2 A,
+                                              float2 B) {
   H32RItem it;
   const unsigned sgn = __float_as_uint(skf) & 0x80000000u;
   const float c = A.x + B.x, d0 = A.y - B.y;  // 2 Re Sx, +-2 Im Sx
   if (MODE == 1) {
     const int k = (int)fabsf(skf);
     col[h32r_phys(k)] = make_float2(0.5f * c, __uint_as_float(__float_as_uint(0.5f * d0) ^ sgn));
+    if (colB) {
+      const float a = A.y + B.y, b0 = B.x - A.x;
+      colB[h32r_phys(k)] = make_float2(0.5f * a, __uint_as_float(__float_as_uint(0.5f * b0) ^ sgn));
+    }
     it.kb = -1;
     it.vre = it.vim = 0.f;
     return it;
@@ -98,7 +105,7 @@ template <int MODE, int SQZ>
 // skf0: signed source bin of step 0; wrapd: increment applied instead of +64 after the step whose
 // source lies in [192, 256) (lanes >= 1: k_a jumps to the mirrored half, -448; lane 0: 192 -> 32).
 __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L, float skf0, float wrapd, float2* xch,
-                                           float2* col, float2 (&va)[8], float2 (&vb)[8]) {
+                                           float2* col, float2* colB, float2 (&va)[8], float2 (&vb)[8]) {
   const int lane = L.lane;
   const bool l0 = L.l0;
   unsigned char* tagA = reinterpret_cast<unsigned char*>(xch);  // tags alias the exchange buffer
@@ -118,7 +125,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
   float skf = skf0;
   {
     H32R_PAIR(0, A, B)
-    cur = h32r_item<MODE, SQZ>(P, col, skf, A, B);
+    cur = h32r_item<MODE, SQZ>(P, col, colB, skf, A, B);
   }
   if (MODE == 0) {
     if (cur.kb >= 0) tagA[cur.kb] = (unsigned char)lane;
@@ -132,7 +139,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
     if (r < 7) {  // next item's arithmetic overlaps this step's tag / accumulator latency
       skf += (skf >= 192.f) ? wrapd : 64.f;
       H32R_PAIR(r + 1, A, B)
-      nxt = h32r_item<MODE, SQZ>(P, col, skf, A, B);
+      nxt = h32r_item<MODE, SQZ>(P, col, colB, skf, A, B);
     }
     if (MODE == 0) {
       unsigned char* T = (r & 1) ? tagB : tagA;
@@ -152,7 +159,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
 #undef H32R_PAIR
   // bin 256 = Z[256] of lane 0 (va[4], self-paired): last, outside the protocol
   if (l0) {
-    const H32RItem it = h32r_item<MODE, SQZ>(P, col, 256.f, va[4], va[4]);
+    const H32RItem it = h32r_item<MODE, SQZ>(P, col, colB, 256.f, va[4], va[4]);
     if (MODE == 0 && it.kb >= 0) smem_rmw_add(col + h32r_phys(it.kb), it.vre, it.vim);
   }
   __syncwarp();  // the tag area is the exchange buffer of the next frame
@@ -171,6 +178,9 @@ __device__ __noinline__ float h32r_edge_sample(const float* x, int64_t n, int64_
 template <int MODE, int SQZ, int NW, bool SLIDE>
 __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(const StftParams P) {
   constexpr int N = 512, AS = H32R_AS, F = 4 * NW;
+  // stft at hop 32: two frames per FFT (z = x_A w + i x_B w; frame B's samples are frame A's window
+  // shifted by one position), so a warp runs 2 FFTs for its 4 frames
+  constexpr bool PAIR = (MODE == 1) && SLIDE;
   extern __shared__ float2 smem[];
   float2* wtab = smem;          // [512] (w, dw*s)
   float2* tw2tab = smem + N;    // [8][9]
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
   int64_t f0 = 0;
   int nfr = 0;
   bool inner = false;
-  float xw[16];
+  float xw[17];  // [16] is only used by PAIR
   // tile indices are 32-bit (checked by the launcher): 64-bit divisions cost ~100 instructions each
   const int tpc = (int)P.tiles_per_channel, ntiles = (int)P.total_tiles;
   auto open_tile = [&](int tile) {  // single call site (see the loop): sets the warp's frames, loads frame f0's window
@@ -230,15 +240,15 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
     f0 += P.frame0;  // from here on f0 is the GLOBAL frame index (sample addressing only)
     xc = P.x + (size_t)ch * P.x_stride;
     const int64_t hop = SLIDE ? 32 : P.hop;
-    inner = f0 * hop - P.left >= 0 && (f0 + 3) * hop + N - 1 - P.left < P.n;
+    inner = f0 * hop - P.left >= 0 && (f0 + 3) * hop + N - 1 - P.left + (PAIR ? 32 : 0) < P.n;
     if (nfr > 0) {
       const int64_t p = f0 * hop + lane;
       if (inner) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) xw[j] = __ldg(xc + (p + 32 * j - P.left));
+        for (int j = 0; j < (PAIR ? 17 : 16); ++j) xw[j] = __ldg(xc + (p + 32 * j - P.left));
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) xw[j] = h32r_edge_sample(xc, P.n, p + 32 * j, P.left, P.padtype);
+        for (int j = 0; j < (PAIR ? 17 : 16); ++j) xw[j] = h32r_edge_sample(xc, P.n, p + 32 * j, P.left, P.padtype);
       }
     }
   };
@@ -253,21 +263,37 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
     const int next = tile + (int)gridDim.x;
     const int my_n = real ? nfr : 0;
 #pragma unroll 1
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 4; s += (PAIR ? 2 : 1)) {
       const bool active = s < my_n;
       float2 va[8], vb[8];
       if (active) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const float2 w0 = wtab[lane + 64 * t], w1 = wtab[lane + 32 + 64 * t];
-          va[t] = make_float2(xw[2 * t] * w0.x, xw[2 * t] * w0.y);
-          vb[t] = make_float2(xw[2 * t + 1] * w1.x, xw[2 * t + 1] * w1.y);
+          if (PAIR) {  // real part frame s, imaginary part frame s+1 (same window, samples one position on)
+            va[t] = make_float2(xw[2 * t] * w0.x, xw[2 * t + 1] * w0.x);
+            vb[t] = make_float2(xw[2 * t + 1] * w1.x, xw[2 * t + 2] * w1.x);
+          } else {
+            va[t] = make_float2(xw[2 * t] * w0.x, xw[2 * t] * w0.y);
+            vb[t] = make_float2(xw[2 * t + 1] * w1.x, xw[2 * t + 1] * w1.y);
+          }
         }
       }
-      if (s == 3) {
+      if (s == (PAIR ? 2 : 3)) {
         if (next < ntiles) open_tile(next);
-      } else if (s + 1 < my_n) {
-        if (SLIDE) {
+      } else if (s + (PAIR ? 2 : 1) < my_n) {
+        if (PAIR) {
+#pragma unroll
+          for (int j = 0; j < 15; ++j) xw[j] = xw[j + 2];
+          const int64_t p = (f0 + s + 2) * 32 + lane + 480;
+          if (inner) {
+            xw[15] = __ldg(xc + (p - P.left));
+            xw[16] = __ldg(xc + (p + 32 - P.left));
+          } else {
+            xw[15] = h32r_edge_sample(xc, P.n, p, P.left, P.padtype);
+            xw[16] = h32r_edge_sample(xc, P.n, p + 32, P.left, P.padtype);
+          }
+        } else if (SLIDE) {
 #pragma unroll
           for (int j = 0; j < 15; ++j) xw[j] = xw[j + 1];
           const int64_t p = (f0 + s + 1) * 32 + lane + 480;
@@ -283,7 +309,9 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
           }
         }
       }
-      if (active) h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, xch, acc + (4 * warp + s) * AS, va, vb);
+      if (active)
+        h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, xch, acc + (4 * warp + s) * AS,
+                              PAIR ? acc + (4 * warp + s + 1) * AS : nullptr, va, vb);
     }
     if (!real) continue;
     __syncthreads();
