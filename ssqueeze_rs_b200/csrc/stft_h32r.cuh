@@ -36,8 +36,8 @@ struct H32RItem {
 // colB != nullptr (stft, hop 32): the FFT carried TWO frames, z = x_A w + i x_B w; the "V" half of the
 // split is then the second frame's spectrum and goes to its own column.
 template <int MODE, int SQZ>
-__device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float2* col, float2* colB, float skf, float2 A,
-                                              float2 B) {
+__device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, float2* col, float2* colB, float skf,
+                                              float2 A, float2 B) {
   H32RItem it;
   const unsigned sgn = __float_as_uint(skf) & 0x80000000u;
   const float c = A.x + B.x, d0 = A.y - B.y;  // 2 Re Sx, +-2 Im Sx
@@ -64,8 +64,8 @@ __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float2* col, 
     it.vre = P.leb_val;
     it.vim = 0.f;
   } else {
-    it.vre = c * P.tx_scale;
-    it.vim = __uint_as_float(__float_as_uint(d0 * P.tx_scale) ^ sgn);
+    it.vre = c * txs;
+    it.vim = __uint_as_float(__float_as_uint(d0 * txs) ^ sgn);
   }
   return it;
 }
@@ -104,8 +104,9 @@ __device__ __noinline__ void h32r_collision(float2* col, unsigned char* T, int k
 template <int MODE, int SQZ>
 // skf0: signed source bin of step 0; wrapd: increment applied instead of +64 after the step whose
 // source lies in [192, 256) (lanes >= 1: k_a jumps to the mirrored half, -448; lane 0: 192 -> 32).
-__device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L, float skf0, float wrapd, float2* xch,
-                                           float2* col, float2* colB, float2 (&va)[8], float2 (&vb)[8]) {
+// txs: dw/2, negated on odd lanes when `modulated` (Sx[k] (-1)^k: every source bin of lane l has l's parity)
+__device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L, float skf0, float wrapd, float txs,
+                                           float2* xch, float2* col, float2* colB, float2 (&va)[8], float2 (&vb)[8]) {
   const int lane = L.lane;
   const bool l0 = L.l0;
   unsigned char* tagA = reinterpret_cast<unsigned char*>(xch);  // tags alias the exchange buffer
@@ -125,7 +126,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
   float skf = skf0;
   {
     H32R_PAIR(0, A, B)
-    cur = h32r_item<MODE, SQZ>(P, col, colB, skf, A, B);
+    cur = h32r_item<MODE, SQZ>(P, txs, col, colB, skf, A, B);
   }
   if (MODE == 0) {
     if (cur.kb >= 0) tagA[cur.kb] = (unsigned char)lane;
@@ -139,7 +140,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
     if (r < 7) {  // next item's arithmetic overlaps this step's tag / accumulator latency
       skf += (skf >= 192.f) ? wrapd : 64.f;
       H32R_PAIR(r + 1, A, B)
-      nxt = h32r_item<MODE, SQZ>(P, col, colB, skf, A, B);
+      nxt = h32r_item<MODE, SQZ>(P, txs, col, colB, skf, A, B);
     }
     if (MODE == 0) {
       unsigned char* T = (r & 1) ? tagB : tagA;
@@ -159,7 +160,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
 #undef H32R_PAIR
   // bin 256 = Z[256] of lane 0 (va[4], self-paired): last, outside the protocol
   if (l0) {
-    const H32RItem it = h32r_item<MODE, SQZ>(P, col, colB, 256.f, va[4], va[4]);
+    const H32RItem it = h32r_item<MODE, SQZ>(P, txs, col, colB, 256.f, va[4], va[4]);
     if (MODE == 0 && it.kb >= 0) smem_rmw_add(col + h32r_phys(it.kb), it.vre, it.vim);
   }
   __syncwarp();  // the tag area is the exchange buffer of the next frame
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
   L.lane_f = (float)lane;
   L.j2_f = (float)L.j2;
   L.l0 = (lane == 0);
+  const float txs = (P.modulated && (lane & 1)) ? -P.tx_scale : P.tx_scale;
   // signed source bin of step r: skf_0, then +64 per step except once (see h32r_frame)
   float skf0, wrapd;
   if (lane == 0) {
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
         }
       }
       if (active)
-        h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, xch, acc + (4 * warp + s) * AS,
+        h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, txs, xch, acc + (4 * warp + s) * AS,
                               PAIR ? acc + (4 * warp + s + 1) * AS : nullptr, va, vb);
     }
     if (!real) continue;
@@ -375,7 +377,7 @@ static ssq_status stft_h32r_launch_nw(ssq_ctx* ctx, StftParams& P, bool* done) {
 
 static ssq_status stft_h32r_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   *done = false;
-  if (P.n_fft != 512 || P.modulated || getenv("SSQ_NO_H32R")) return SSQ_OK;
+  if (P.n_fft != 512 || getenv("SSQ_NO_H32R")) return SSQ_OK;
   if (P.hop != 32 && getenv("SSQ_H32R_HOP32_ONLY")) return SSQ_OK;
   static const int nw_env = getenv("SSQ_H32R_NW") ? atoi(getenv("SSQ_H32R_NW")) : 4;
   if (nw_env == 4) SSQ_TRY(stft_h32r_launch_nw<4>(ctx, P, done));

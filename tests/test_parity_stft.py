@@ -470,3 +470,21 @@ def test_istft_512_any_hop(hop, N):
         assert "istft512_tile" in _lib.default_context().last_kernel_name()
         xo = O.istft(So, win, n_fft=512, hop_len=hop, N=N, win_exp=wexp)
         assert np.abs(xr - xo).max() < RTOL * max(np.abs(xo).max(), 1e-30), (hop, wexp)
+
+
+def test_modulated_fast_path_and_issq_roundtrip_512():
+    """`modulated=True` (Sx[k] (-1)^k before squeezing) on the n_fft=512 fast kernel, hop 1 and 32, and the
+    issq_stft round trip (old/tests/reconstruction_test.py:182-206: MAE < 0.1) at n_fft=512."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    x = np.random.default_rng(77).standard_normal(1500)
+    win = np.hanning(514)[1:-1].copy()
+    for hop in (1, 32):
+        Tx, _ = rs.ssq_stft(x, win, n_fft=512, hop_len=hop, fs=250.0, modulated=True)
+        assert "h32r" in _lib.default_context().last_kernel_name()
+        To, _ = O.ssq_stft(x, win, n_fft=512, hop_len=hop, fs=250.0, modulated=True)
+        _flip_tolerant_compare(Tx, To, max_bad_frac=4e-3)
+    Tx, _ = rs.ssq_stft(x, win, n_fft=512, hop_len=1, fs=250.0, modulated=True)
+    y = rs.issq_stft(Tx, win, n_fft=512, hop_len=1, fs=250.0)
+    sh = 512 // 2 - (512 - 1) // 2
+    assert np.abs(y[:len(x) - sh] - x[sh:]).mean() < 0.1
