@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_h32_kernel(const I
 // ------------------------------------------------------------------------------------
 #define I32T_AS 289  // tile row stride (float2): odd -> conflict-free transposed tile load; 578 floats >= 512
 
+template <bool HOP32>  // hop == 32: shifts instead of integer divisions in the gather
 __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const Istft32Params P) {
   constexpr int N = 512, AS = I32T_AS, F = 32;
   extern __shared__ float2 smem[];
@@ -286,14 +287,14 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const 
     __syncthreads();
     // ---- overlap-add gather over the tile span, one red per padded sample ---------------------------
     {
-      const int hop = P.hop;
+      const int hop = HOP32 ? 32 : P.hop;
       const int span = (nf - 1) * hop + N;
       float* xo = P.xacc + (size_t)ch * P.L + f0 * hop;
       const int64_t room = P.L - f0 * hop;
       const float* Sf = reinterpret_cast<const float*>(S);
       for (int p = threadIdx.x; p < span; p += blockDim.x) {
-        const int fhi = min(nf - 1, p / hop);
-        const int flo = p < N ? 0 : (p - N + hop) / hop;  // ceil((p - N + 1) / hop)
+        const int fhi = min(nf - 1, HOP32 ? (p >> 5) : p / hop);
+        const int flo = p < N ? 0 : (HOP32 ? ((p - N + 32) >> 5) : (p - N + hop) / hop);  // ceil((p - N + 1) / hop)
         float acc = 0.f;
         for (int f = flo; f <= fhi; ++f) acc += Sf[f * (2 * AS) + (p - hop * f)];
         if (p < room && flo <= fhi) atomicAdd(xo + p, acc);

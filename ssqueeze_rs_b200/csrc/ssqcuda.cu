@@ -484,8 +484,9 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
       Q.total_runs = Q.runs_per_channel * channels;
       const size_t smem = ((size_t)72 + (size_t)32 * I32T_AS + (size_t)H32_WARPS * 512) * sizeof(float2);
       const int grid = (int)std::min<int64_t>(Q.total_runs, (int64_t)ctx->num_sms * 2);
-      SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(istft512_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      istft512_tile_kernel<<<grid, H32_WARPS * 32, smem, ctx->stream>>>(Q);
+      void (*k)(const Istft32Params) = hop == 32 ? istft512_tile_kernel<true> : istft512_tile_kernel<false>;
+      SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, H32_WARPS * 32, smem, ctx->stream>>>(Q);
       SSQ_TRY(ssq_check_launch(ctx, "istft512_tile_kernel"));
       ctx->last_kernel = "istft512_tile_kernel";
     }

@@ -118,7 +118,9 @@ struct H32Lane {
 // 512-point forward DFT of one frame: inputs va[t] = z[lane + 64 t], vb[t] = z[lane + 32 + 64 t];
 // outputs va[m] = Z[lane + 64 m], vb[m] = Z[L.j2 + 64 m].  Two swizzled exchanges through xch.
 // ROT: the last butterfly of vb uses the conjugate kernel (see stft_h32r.cuh).
-template <bool ROT = false>
+// TW2POW: stage-2 twiddles by powers of one table entry (saves 12 shared-memory wavefronts, costs 24
+// multiplies: a gain where the data pipe binds -- stft/ssq_stft -- and a loss for istft).
+template <bool ROT = false, bool TW2POW = ROT>
 __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2 (&va)[8], float2 (&vb)[8]) {
   const int lane = L.lane, j2 = L.j2;
   fft8_fwd(va);
@@ -141,16 +143,19 @@ __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2
   }
   __syncwarp();
   {
-    // W_64^{r t}, r = lane & 7: one table read, the other powers by products at most 3 deep
-    // (6 complex multiplies instead of 6 more shared-memory reads: the data pipe is the binding resource)
     float2 w[8];
-    w[1] = L.tw2[1];
-    w[2] = cmulf(w[1], w[1]);
-    w[3] = cmulf(w[2], w[1]);
-    w[4] = cmulf(w[2], w[2]);
-    w[5] = cmulf(w[4], w[1]);
-    w[6] = cmulf(w[4], w[2]);
-    w[7] = cmulf(w[4], w[3]);
+    w[1] = L.tw2[1];  // W_64^{r t}, r = lane & 7
+    if (TW2POW) {     // the other powers by products at most 3 deep
+      w[2] = cmulf(w[1], w[1]);
+      w[3] = cmulf(w[2], w[1]);
+      w[4] = cmulf(w[2], w[2]);
+      w[5] = cmulf(w[4], w[1]);
+      w[6] = cmulf(w[4], w[2]);
+      w[7] = cmulf(w[4], w[3]);
+    } else {
+#pragma unroll
+      for (int t = 2; t < 8; ++t) w[t] = L.tw2[t];
+    }
 #pragma unroll
     for (int t = 1; t < 8; ++t) {
       va[t] = cmulf(va[t], w[t]);
@@ -206,7 +211,7 @@ __device__ __forceinline__ void h32_frame(const StftParams& P, const H32Lane& L,
   int* skey = reinterpret_cast<int*>(sre + 528);                        // [264]
   unsigned char* tagA = reinterpret_cast<unsigned char*>(sre + 792);    // [264]
   unsigned char* tagB = tagA + 264;                                     // [264]
-  h32_fft512(L, xch, va, vb);
+  h32_fft512<false, true>(L, xch, va, vb);
 
   // ---- split + phase transform: lane owns bins lane+64m and j2+64m (and lane 0: 256) ------
   const bool l0 = L.l0;
