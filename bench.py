@@ -316,6 +316,78 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_other(args, rank, world, local_rank):
+    """Device-resident timing of the other rows of SURVEY 8 (not the contract line)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ssqueeze_rs_b200.batch import Engine
+    from ssqueeze_rs_b200.dist import job_throughput
+    eng = Engine(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5351 + rank)
+    win = np.hanning(N_FFT)
+    wl = args.workload
+    if wl == "istft":
+        ch, n = (4096, 300_000) if args.channels == CHANNELS else (args.channels, args.samples)
+        x = torch.randn((ch, n), generator=g, device=dev) * 10
+        Sx = eng.stft(x, win, N_FFT, HOP)
+        nfr = Sx.shape[2]
+        abytes = ch * (4 * n + 8 * (N_FFT // 2 + 1) * nfr)
+        desc = f"istft {ch}ch x {n} samples, n_fft=512 hop=32 (overlap-add + window norm + unpad)"
+        step = lambda: eng.istft(Sx, win, N_FFT, HOP, N=n)
+    elif wl == "stft":
+        ch, n = args.channels, args.samples
+        x = make_neural(torch, ch, n, FS, dev, 0x5351 + rank)
+        out = torch.empty((ch, N_FFT // 2 + 1, (n - 1) // HOP + 1), dtype=torch.complex64, device=dev)
+        abytes = algorithmic_bytes(ch, n)
+        desc = f"stft {ch}ch x {n} samples, n_fft=512 hop=32"
+        step = lambda: eng.stft(x, win, N_FFT, HOP, out=out)
+    else:
+        ch, n = (8, 1 << 20) if args.channels == CHANNELS else (args.channels, args.samples)
+        t = torch.arange(n, device=dev, dtype=torch.float64) / n
+        chirp = torch.sin(2 * np.pi * n * (0.001 * t + 0.5 * 0.399 * t * t)).to(torch.float32)
+        x = chirp.view(1, -1) + 0.5 * torch.randn((ch, n), generator=g, device=dev)
+        import ctypes as C
+        from ssqueeze_rs_b200._lib import load
+        ns = load().ssq_cwt_default_scales(n, 32, 0, C.c_void_p(0))
+        out = torch.empty((ch, ns, n), dtype=torch.complex64, device=dev)
+        abytes = ch * (4 * n + 8 * ns * n)
+        desc = f"ssq_cwt gmw nv=32 ({ns} scales) on {ch}ch x {n} chirp+noise (channel cut of configs[2])"
+        step = lambda: eng.ssq_cwt(x, "gmw", None, fs=1.0, nv=32, maprange="maximal", out=out)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    per_s, total_ms = job_throughput(float(ch) * n * args.steps, ev0.elapsed_time(ev1), dev)
+    peak, peak_src = measured_peak_gbs()
+    ms = total_ms / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"{wl} input Msamples/s", "value": per_s / 1e6, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": desc},
+            "roofline": {"bound": "hbm", "achieved": abytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": abytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "whole step (all kernels of the call), not one kernel"},
+            "kernel": eng.last_kernel_name()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_e2e(eng, args, rank, world, window, x_dev, dev):
     """Host pinned x -> [H2D, kernel, D2H] -> host pinned Tx, every step."""
     import torch
@@ -376,6 +448,10 @@ def main():
     ap.add_argument("--e2e-channels", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-samples", type=int, default=450_000, help="samples per step of the reference arm")
+    ap.add_argument("--workload", default="ssq_stft", choices=["ssq_stft", "stft", "istft", "ssq_cwt"],
+                    help="ssq_stft (default, BASELINE configs[1]) is the contract line; the others time the "
+                         "remaining rows of SURVEY 8 (configs[3] istft 4096 ch x 300 k, configs[2] ssq_cwt on a "
+                         "channel cut of 2^20 samples, stft on configs[1]) with the same JSON layout")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -383,6 +459,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload != "ssq_stft":
+        run_other(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -379,7 +379,10 @@ static ssq_status stft_h32r_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   *done = false;
   if (P.n_fft != 512 || getenv("SSQ_NO_H32R")) return SSQ_OK;
   if (P.hop != 32 && getenv("SSQ_H32R_HOP32_ONLY")) return SSQ_OK;
-  static const int nw_env = getenv("SSQ_H32R_NW") ? atoi(getenv("SSQ_H32R_NW")) : 4;
+  // 4-warp CTAs (16-frame tiles, 128 B row segments) win for ssq_stft; the faster stft mode writes at
+  // > 2.5 TB/s and needs the 256 B segments of the 8-warp shape at full scale (384 channels: 18.1 vs 26.5 ms)
+  static const int nw_force = getenv("SSQ_H32R_NW") ? atoi(getenv("SSQ_H32R_NW")) : 0;
+  const int nw_env = nw_force ? nw_force : (P.mode == 1 ? 8 : 4);
   if (nw_env == 4) SSQ_TRY(stft_h32r_launch_nw<4>(ctx, P, done));
   else SSQ_TRY(stft_h32r_launch_nw<8>(ctx, P, done));
   return SSQ_OK;
