@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
         for (int ii = 0; ii < 8; ++ii) {
           const float2 val = a[8 * ii];
           if (MODE == 0) a[8 * ii] = make_float2(0.f, 0.f);
-          if (ok) *g = val;
+          if (ok) __stcs(g, val);
           g += gstep;
         }
         a += 65;
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
       if (v == 0) {  // row 256 at physical 260 (a has advanced by 4 * 65)
         const float2 val = a[0];
         if (MODE == 0) a[0] = make_float2(0.f, 0.f);
-        if (ok) *g = val;
+        if (ok) __stcs(g, val);
       }
     }
     __syncthreads();
