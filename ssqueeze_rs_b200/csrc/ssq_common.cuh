@@ -107,17 +107,19 @@ __device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2
 
 // Padded-signal sample fetch in the reference's STFT framing
 // (stft_utils.rs:19-65): padded index p, left = (n_fft-1)/2.
+// `origin`: global index of x[0] (streaming: x holds the samples [origin, ...) of a longer recording of
+// n samples; every index that is read lies inside the carried-over buffer).
 __device__ __forceinline__ float stft_sample(const float* __restrict__ x, int64_t n, int64_t p,
-                                             int left, int padtype) {
+                                             int left, int padtype, int64_t origin = 0) {
   int64_t o = p - left;
-  if (o >= 0 && o < n) return __ldg(x + o);
+  if (o >= 0 && o < n) return __ldg(x + (o - origin));
   if (padtype == SSQ_PAD_ZERO) return 0.f;
   if (o < 0) {
     int64_t m = -o;  // stft_utils.rs:34-36
-    return m < n ? __ldg(x + m) : 0.f;
+    return m < n ? __ldg(x + (m - origin)) : 0.f;
   }
   int64_t m = 2 * n - 2 - o;  // stft_utils.rs:42-44
-  return (m >= 0 && m < n) ? __ldg(x + m) : 0.f;
+  return (m >= 0 && m < n) ? __ldg(x + (m - origin)) : 0.f;
 }
 
 // Non-atomic-free float2 accumulate in shared memory: fp32 shared atomics are

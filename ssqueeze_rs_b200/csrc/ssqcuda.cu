@@ -282,9 +282,10 @@ struct StftCall {
   float2* aux_dSx;
   float* aux_w;
   // streaming (ssq_stream_*): compute frames [frame0, frame0 + n_frames_call) of a recording of n
-  // samples; d_x is then a VIRTUAL base pointer indexed by global sample position
+  // samples, of which d_x holds [x_origin, ...)
   int64_t frame0 = 0;
   int64_t n_frames_call = 0;
+  int64_t x_origin = 0;  // global sample index of d_x[.][0]
 };
 
 static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
@@ -314,6 +315,7 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   P.is_pow2 = P.log2n >= 0;
   P.n_frames = n_frames;
   P.frame0 = c.frame0;
+  P.x_origin = c.x_origin;
   P.left = (N - 1) / 2;
   P.padtype = c.padtype == SSQ_PAD_ZERO ? SSQ_PAD_ZERO : SSQ_PAD_REFLECT;
   P.win = T.win;
@@ -892,7 +894,8 @@ static ssq_status stream_push(ssq_stream* s, const T* d_chunk, int64_t n_new, fl
     if (!d_Tx) return ssq_fail(ctx, SSQ_EINVAL, "d_Tx is NULL but %lld frames are ready", (long long)count);
     StftCall c;
     c.mode = 0;
-    c.d_x = buf - s->origin;  // virtual base: indexed by global sample position
+    c.d_x = buf;
+    c.x_origin = s->origin;
     c.channels = s->channels;
     c.n = s->n_total;
     c.x_stride = s->cap;

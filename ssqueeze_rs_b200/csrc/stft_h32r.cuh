@@ -168,8 +168,9 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
 
 // Edge tiles only (reflect / zero padding index map); kept out of line: the main loop has to fit the
 // instruction cache (the fully inlined version was 88 KB of SASS, 7 % of the issue slots starved).
-__device__ __noinline__ float h32r_edge_sample(const float* x, int64_t n, int64_t p, int left, int padtype) {
-  return stft_sample(x, n, p, left, padtype);
+__device__ __noinline__ float h32r_edge_sample(const float* x, int64_t n, int64_t p, int left, int padtype,
+                                               int64_t origin) {
+  return stft_sample(x, n, p, left, padtype, origin);
 }
 
 // NW warps per CTA (8: 32-frame tile, 2 CTAs per SM; 4: 16-frame tile, 4 CTAs per SM -- the same 16
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
   int nfr = 0;
   bool inner = false;
   float xw[17];  // [16] is only used by PAIR
+  const int64_t lo = P.left + P.x_origin;  // padded position p of an interior sample lives at x[p - lo]
   // tile indices are 32-bit (checked by the launcher): 64-bit divisions cost ~100 instructions each
   const int tpc = (int)P.tiles_per_channel, ntiles = (int)P.total_tiles;
   auto open_tile = [&](int tile) {  // single call site (see the loop): sets the warp's frames, loads frame f0's window
@@ -247,10 +249,10 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
       const int64_t p = f0 * hop + lane;
       if (inner) {
 #pragma unroll
-        for (int j = 0; j < (PAIR ? 17 : 16); ++j) xw[j] = __ldg(xc + (p + 32 * j - P.left));
+        for (int j = 0; j < (PAIR ? 17 : 16); ++j) xw[j] = __ldg(xc + (p + 32 * j - lo));
       } else {
 #pragma unroll
-        for (int j = 0; j < (PAIR ? 17 : 16); ++j) xw[j] = h32r_edge_sample(xc, P.n, p + 32 * j, P.left, P.padtype);
+        for (int j = 0; j < (PAIR ? 17 : 16); ++j) xw[j] = h32r_edge_sample(xc, P.n, p + 32 * j, P.left, P.padtype, P.x_origin);
       }
     }
   };
@@ -289,25 +291,25 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
           for (int j = 0; j < 15; ++j) xw[j] = xw[j + 2];
           const int64_t p = (f0 + s + 2) * 32 + lane + 480;
           if (inner) {
-            xw[15] = __ldg(xc + (p - P.left));
-            xw[16] = __ldg(xc + (p + 32 - P.left));
+            xw[15] = __ldg(xc + (p - lo));
+            xw[16] = __ldg(xc + (p + 32 - lo));
           } else {
-            xw[15] = h32r_edge_sample(xc, P.n, p, P.left, P.padtype);
-            xw[16] = h32r_edge_sample(xc, P.n, p + 32, P.left, P.padtype);
+            xw[15] = h32r_edge_sample(xc, P.n, p, P.left, P.padtype, P.x_origin);
+            xw[16] = h32r_edge_sample(xc, P.n, p + 32, P.left, P.padtype, P.x_origin);
           }
         } else if (SLIDE) {
 #pragma unroll
           for (int j = 0; j < 15; ++j) xw[j] = xw[j + 1];
           const int64_t p = (f0 + s + 1) * 32 + lane + 480;
-          xw[15] = inner ? __ldg(xc + (p - P.left)) : h32r_edge_sample(xc, P.n, p, P.left, P.padtype);
+          xw[15] = inner ? __ldg(xc + (p - lo)) : h32r_edge_sample(xc, P.n, p, P.left, P.padtype, P.x_origin);
         } else {
           const int64_t p = (f0 + s + 1) * (int64_t)P.hop + lane;
           if (inner) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) xw[j] = __ldg(xc + (p + 32 * j - P.left));
+            for (int j = 0; j < 16; ++j) xw[j] = __ldg(xc + (p + 32 * j - lo));
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) xw[j] = h32r_edge_sample(xc, P.n, p + 32 * j, P.left, P.padtype);
+            for (int j = 0; j < 16; ++j) xw[j] = h32r_edge_sample(xc, P.n, p + 32 * j, P.left, P.padtype, P.x_origin);
           }
         }
       }

@@ -43,8 +43,8 @@ struct StftParams {
   float2* aux_dSx;      // optional
   float* aux_w;         // optional (Hz, +inf where gated)
   int64_t frame0;       // global index of local frame 0 (streaming: the call computes frames
-                        // [frame0, frame0 + n_frames) of a longer recording; x is then addressed by
-                        // GLOBAL sample index and n is the total length, see ssq_stream_* in ssqcuda.cu)
+                        // [frame0, frame0 + n_frames) of a recording of n samples, see ssq_stream_*)
+  int64_t x_origin;     // global sample index of x[.][0] (0 unless streaming)
   int F;                // frames per tile
   int acc_stride;       // odd >= n_freqs
   int64_t tiles_per_channel, total_tiles;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
       float2* A = work;
       float2* B = work + N;
       for (int n = lane; n < N; n += 32) {
-        float xv = stft_sample(xc, P.n, start + n, P.left, P.padtype);
+        float xv = stft_sample(xc, P.n, start + n, P.left, P.padtype, P.x_origin);
         A[n] = make_float2(xv * P.win[n], xv * P.dwin[n]);
       }
       __syncwarp();
