@@ -191,6 +191,27 @@ def cpu_reference_run(n_samples, steps, warmup, mode=0, channels=1):
     return channels * n_samples / (sum(times) / len(times)) / 1e6, cref.num_threads(), sum(times) / len(times)
 
 
+def parity_gates(eng, torch, dev, n_samples=400_000):
+    """SURVEY 8(d) parity gates, reported beside the throughput: the CUDA path against the C restatement
+    (the checker, part of the cpu_baseline leg) on one channel of the same synthetic recipe."""
+    from oracle import cref
+    x = make_neural_cpu(1, n_samples, FS, 0x5351 + 7)
+    w = np.hanning(N_FFT)
+    ref, _ = cref.ssq_stft(x[0], w, N_FFT, HOP, FS, mode=1)
+    xd = torch.from_numpy(x.astype(np.float32)).to(dev)
+    got = eng.ssq_stft(xd, w, n_fft=N_FFT, hop_len=HOP, fs=FS)[0].cpu().numpy().astype(np.complex128)
+    torch.cuda.synchronize()
+    scale = float(np.abs(ref).max())
+    d = np.abs(got - ref)
+    ok = d <= 1e-4 * scale + 1e-4 * np.abs(ref)
+    # energy that moved to another bin shows up twice in |got - ref|; column sums are invariant to it
+    cs = np.abs(got.sum(axis=0) - ref.sum(axis=0)).max() / np.abs(ref.sum(axis=0)).max()
+    return {"against": "oracle/ssq_stft_ref.c (f64), 1 channel x %d samples" % n_samples,
+            "rel_max_abs_err": float(d.max() / scale), "frac_within_rtol_1e-4": float(ok.mean()),
+            "bins_differing": int((~ok).sum()), "bins_total": int(ok.size),
+            "column_sum_rel_err": float(cs)}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -291,7 +312,9 @@ def run_ours(args, rank, world, local_rank):
     e2e = run_e2e(eng, args, rank, world, window, x, dev)
 
     cpu_baseline = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        parity = parity_gates(eng, torch, dev)
         msps, threads, sec = cpu_reference_run(900_000, 1, 0, mode=0)
         msps_i, _, sec_i = cpu_reference_run(900_000, 1, 1, mode=1, channels=2)
         cpu_baseline = {"value": msps, "unit": "Msamples/s", "cores": threads, "kind": "port",
@@ -309,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
                        "hop": HOP, "fs": FS, "parallelism": f"channel-shard x{world}, no collective",
                        "l2_policy": "inputs (2.8 GB) and outputs (44 GB) per step exceed the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "checksum": chk,
+            "cpu_baseline": cpu_baseline, "parity": parity, "checksum": chk,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -68,7 +68,10 @@ enum {
   SSQ_FLAG_NO_FLIPUD = 1u << 1,  /* ssq_cwt: flipud=false (ssq_cwt.rs:180-184) */
   SSQ_FLAG_L2_NORM = 1u << 2,    /* cwt: l1_norm=false -> multiply rows by sqrt(scale) (cwt.rs:253) */
   SSQ_FLAG_RPADDED = 1u << 3,    /* cwt: return the padded [ns, pad_len] rows (cwt.rs:108-110) */
-  SSQ_FLAG_SIMD_SCALES = 1u << 4 /* cwt_simd default-scale generator (cwt_simd.rs:489-527) */
+  SSQ_FLAG_SIMD_SCALES = 1u << 4, /* cwt_simd default-scale generator (cwt_simd.rs:489-527) */
+  SSQ_FLAG_ADM_EXACT = 1u << 5    /* icwt: divide by the wavelet's true admissibility integral
+                                     (ssq_cwt_admissibility) instead of the reference's placeholders
+                                     0.776 / 1.0 (cwt.rs:579-583), so that cwt -> icwt reconstructs x */
 };
 
 /* ---- library / context ------------------------------------------------- */
@@ -150,10 +153,22 @@ ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet
 /* `icwt`: cwt.rs:548-718, a #[pyfunction] the reference module never registers.
  * One-integral branch (:590-627, the default): x[j] = (2/adm) dj sum_i Re Wx[i,j] norm_i + x_mean.
  * one_int == 0 (two-integral, FFTs of arbitrary length x_len) returns SSQ_EUNSUPPORTED.
- * Wx complex128 [ns, n_cols] -> x float64 [x_len] (x_len <= 0: n_cols).  flags: SSQ_FLAG_L2_NORM. */
+ * Wx complex128 [ns, n_cols] -> x float64 [x_len] (x_len <= 0: n_cols).
+ * flags: SSQ_FLAG_L2_NORM, SSQ_FLAG_ADM_EXACT. */
 ssq_status ssq_icwt_f64(ssq_ctx* ctx, const double* Wx, int64_t ns, int64_t n_cols, int wavelet,
                         const double* scales, int one_int, int64_t x_len, double x_mean, unsigned flags,
                         double* x);
+
+/* Css = integral psi-hat(w)/w dw of the wavelet ssq_cwt/cwt evaluate (cwt.rs:492-547; definition
+ * old/ssqueezepy/utils/cwt_utils.py:28-47).  Host-side, double. */
+ssq_status ssq_cwt_admissibility(int wavelet, double* css);
+
+/* `issq_cwt` (spec old/ssqueezepy/_ssq_cwt.py:313-378, full inversion):
+ * x[j] = (2/Css) dj sum_k Re Tx[k,j], dj = ln(scales[1]/scales[0]) (0.1 if not ascending, as icwt).
+ * The dj factor is upstream's `const` (ln 2 / nv), which the reference's ssqueeze leaves out of Tx
+ * (ssq_cwt.rs:116-222).  Tx complex128 [ns, n] -> x float64 [n]. */
+ssq_status ssq_issq_cwt_f64(ssq_ctx* ctx, const double* Tx, int64_t ns, int64_t n, int wavelet,
+                            const double* scales, double* x);
 
 /* ---- batched throughput path (device buffers, fp32 / complex64) ---------- */
 /* replaces the per-channel Python loop around `_rs.ssq_stft`
@@ -193,6 +208,10 @@ ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channel
 ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_t channels, int64_t ns, int64_t n_cols,
                               int wavelet, const double* scales, int one_int, int64_t x_len, double x_mean,
                               unsigned flags, float* d_x);
+
+/* d_Tx complex64 [channels, ns, n] -> d_x fp32 [channels, n] */
+ssq_status ssq_issq_cwt_batch_f32(ssq_ctx* ctx, const float* d_Tx, int64_t channels, int64_t ns, int64_t n,
+                                  int wavelet, const double* scales, float* d_x);
 
 /* ---- batched path with HOST buffers (copies inside; synchronous) --------- */
 /* x: host fp32 [channels, n]; Tx: host complex64 [channels, n_freqs, n_frames] */

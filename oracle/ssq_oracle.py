@@ -498,8 +498,32 @@ def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=3
 # --------------------------------------------------------------------------
 # icwt (cwt.rs:548-718, a #[pyfunction] the module never registers)
 # --------------------------------------------------------------------------
+def adm_ssq(wavelet="gmw"):
+    """Css = integral_0^inf psi-hat(w)/w dw (old/ssqueezepy/utils/cwt_utils.py:28-47) of the wavelet
+    generate_wavelet_fourier evaluates (cwt.rs:492-547), by adaptive quadrature."""
+    from scipy.integrate import quad
+    one = np.ones(1)
+    f = lambda w: float(generate_wavelet_fourier(one * w, 1.0, wavelet)[0].real) / w
+    pts = [6.0] if wavelet == "morlet" else [20.0 ** (1.0 / 3.0)]
+    return quad(f, 1e-12, 60.0, points=pts, epsabs=0.0, epsrel=1e-13, limit=2000)[0]
+
+
+def issq_cwt(Tx, wavelet="gmw", scales=None):
+    """old/ssqueezepy/_ssq_cwt.py:313-378 (full inversion) in the reference's framing: the log-step `const`
+    upstream bakes into Tx is applied here (the reference's ssqueeze omits it, ssq_cwt.rs:116-222)."""
+    Tx = np.asarray(Tx, dtype=np.complex128)
+    if scales is None:
+        raise ValueError("Scales must be provided")
+    scales = np.asarray(scales, dtype=np.float64)
+    dj = math.log(scales[1] / scales[0]) if (len(scales) > 1 and scales[1] > scales[0]) else 0.1
+    x = np.zeros(Tx.shape[1])
+    for i in range(Tx.shape[0]):
+        x += Tx[i].real
+    return x * (2.0 / adm_ssq(wavelet)) * dj
+
+
 def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_mean=0.0,
-         padtype="reflect", rpadded=False, l1_norm=True):
+         padtype="reflect", rpadded=False, l1_norm=True, exact_adm=False):
     """cwt.rs:548-718.  Only the one-integral branch (:590-627, the default) is restated: the
     two-integral branch needs FFTs of arbitrary length x_len and is not built (SSQ_EUNSUPPORTED)."""
     Wx = np.asarray(Wx, dtype=np.complex128)
@@ -508,6 +532,8 @@ def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_me
     scales = np.asarray(scales, dtype=np.float64)
     n_scales, n_times = Wx.shape
     adm = 0.776 if wavelet == "morlet" else 1.0       # cwt.rs:579-583
+    if exact_adm:
+        adm = adm_ssq(wavelet)
     x_length = n_times if x_len is None else int(x_len)
     if x_length > n_times:
         raise IndexError("x_len > Wx.shape[1]: ndarray index out of bounds (panic) at cwt.rs:613")

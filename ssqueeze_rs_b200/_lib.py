@@ -28,7 +28,7 @@ SSQ_OK, SSQ_EINVAL, SSQ_ECUDA, SSQ_ENOMEM, SSQ_EUNSUPPORTED, SSQ_EPANIC = range(
 
 PAD = {"reflect": 0, "zero": 1}
 SQUEEZE = {"sum": 0, "lebesgue": 1}
-FLAG_MODULATED, FLAG_NO_FLIPUD, FLAG_L2_NORM, FLAG_RPADDED, FLAG_SIMD_SCALES = 1, 2, 4, 8, 16
+FLAG_MODULATED, FLAG_NO_FLIPUD, FLAG_L2_NORM, FLAG_RPADDED, FLAG_SIMD_SCALES, FLAG_ADM_EXACT = 1, 2, 4, 8, 16, 32
 
 c_i64, c_int, c_dbl, c_u32, c_vp = C.c_int64, C.c_int, C.c_double, C.c_uint, C.c_void_p
 P_dbl = C.POINTER(C.c_double)
@@ -57,6 +57,9 @@ SIGNATURES = {
     "ssq_ssq_cwt_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_dbl, c_int, c_int, c_int, c_int,
                                 c_dbl, c_u32, c_vp, c_vp]),
     "ssq_icwt_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_i64, c_dbl, c_u32, c_vp]),
+    "ssq_cwt_admissibility": (c_int, [c_int, c_vp]),
+    "ssq_issq_cwt_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
+    "ssq_issq_cwt_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp]),
     "ssq_icwt_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_int, c_i64, c_dbl, c_u32, c_vp]),
     "ssq_ssq_stft_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl,
                                        c_int, c_int, c_dbl, c_u32, c_vp]),

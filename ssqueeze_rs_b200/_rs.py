@@ -18,10 +18,11 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (FLAG_L2_NORM, FLAG_MODULATED, FLAG_NO_FLIPUD, FLAG_RPADDED, FLAG_SIMD_SCALES, PAD, SQUEEZE,
+from ._lib import (FLAG_ADM_EXACT, FLAG_L2_NORM, FLAG_MODULATED, FLAG_NO_FLIPUD, FLAG_RPADDED, FLAG_SIMD_SCALES, PAD, SQUEEZE,
                    default_context, load, raise_status)
 
-__all__ = ["hello_from_bin", "stft", "ssq_stft", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt", "icwt"]
+__all__ = ["hello_from_bin", "stft", "ssq_stft", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt", "icwt", "issq_cwt",
+           "adm_ssq"]
 
 
 def _f64_1d(a, name):
@@ -233,9 +234,11 @@ def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=3
 
 
 def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_mean=0.0, padtype="reflect",
-         rpadded=False, l1_norm=True):
+         rpadded=False, l1_norm=True, exact_adm=False):
     """cwt.rs:548-566 (declared in src/ssqueeze/_rs.pyi:62-73, never registered by lib.rs:25-32).
-    One-integral reconstruction; `nv`, `padtype`, `rpadded` are accepted and unused as in the reference."""
+    One-integral reconstruction; `nv`, `padtype`, `rpadded` are accepted and unused as in the reference.
+    `exact_adm=True` (not in the reference) divides by the wavelet's true admissibility integral
+    (`adm_ssq`) instead of the placeholders 0.776 / 1.0 of cwt.rs:579-583, so that `icwt(cwt(x))` returns x."""
     if not isinstance(Wx, np.ndarray) or Wx.ndim != 2 or Wx.dtype != np.complex128:
         raise TypeError("argument 'Wx': expected a 2-D numpy.ndarray of complex128")
     if scales is None:
@@ -249,6 +252,37 @@ def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_me
     x = np.empty(max(xl, 0), dtype=np.float64)
     ctx = default_context()
     st = load().ssq_icwt_f64(ctx.handle, _ptr(Wx), ns, ncols, 1 if _str(wavelet, "wavelet") == "morlet" else 0,
-                             _ptr(sc), 1 if one_int else 0, xl, float(x_mean), 0 if l1_norm else FLAG_L2_NORM, _ptr(x))
+                             _ptr(sc), 1 if one_int else 0, xl, float(x_mean),
+                             (0 if l1_norm else FLAG_L2_NORM) | (FLAG_ADM_EXACT if exact_adm else 0), _ptr(x))
+    raise_status(st, ctx.handle)
+    return x
+
+
+def adm_ssq(wavelet="gmw"):
+    """Css = integral psi-hat(w)/w dw of the wavelet `cwt`/`ssq_cwt` evaluate (cwt.rs:492-547); definition
+    old/ssqueezepy/utils/cwt_utils.py:28-47."""
+    import ctypes
+    out = ctypes.c_double(0.0)
+    st = load().ssq_cwt_admissibility(1 if _str(wavelet, "wavelet") == "morlet" else 0, ctypes.addressof(out))
+    if st != 0:
+        raise RuntimeError("ssq_cwt_admissibility failed")
+    return out.value
+
+
+def issq_cwt(Tx, wavelet="gmw", scales=None):
+    """Full inversion of `ssq_cwt` (spec old/ssqueezepy/_ssq_cwt.py:313-378; absent from the reference crate):
+    x = (2/Css) ln(scales[1]/scales[0]) sum_k Re Tx[k].  `scales` are the ones `ssq_cwt` used; the log-step
+    factor is upstream's `const`, which the reference's ssqueeze leaves out of Tx (ssq_cwt.rs:116-222)."""
+    if not isinstance(Tx, np.ndarray) or Tx.ndim != 2 or Tx.dtype != np.complex128:
+        raise TypeError("argument 'Tx': expected a 2-D numpy.ndarray of complex128")
+    if scales is None:
+        raise ValueError("Scales must be provided")
+    sc = _f64_1d(scales, "scales")
+    Tx = np.ascontiguousarray(Tx)
+    ns, n = Tx.shape
+    x = np.empty(n, dtype=np.float64)
+    ctx = default_context()
+    st = load().ssq_issq_cwt_f64(ctx.handle, _ptr(Tx), ns, n, 1 if _str(wavelet, "wavelet") == "morlet" else 0,
+                                 _ptr(sc), _ptr(x))
     raise_status(st, ctx.handle)
     return x

@@ -444,7 +444,8 @@ extern "C" ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_
   if (!one_int)
     return ssq_fail(ctx, SSQ_EUNSUPPORTED, "icwt: the two-integral branch (cwt.rs:629-712) is not built; use one_int=True");
   SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const double adm = wavelet == SSQ_WAVELET_MORLET ? 0.776 : 1.0;                                   // cwt.rs:579-583
+  const double adm = (flags & SSQ_FLAG_ADM_EXACT) ? ssqhost::admissibility_ssq(wavelet == SSQ_WAVELET_MORLET)
+                     : wavelet == SSQ_WAVELET_MORLET ? 0.776 : 1.0;                                 // cwt.rs:579-583
   const double dj = (ns > 1 && scales[1] > scales[0]) ? std::log(scales[1] / scales[0]) : 0.1;     // :595-599
   const double final_norm = (2.0 / adm) * dj;
   std::vector<float> hn((size_t)ns);
@@ -479,4 +480,49 @@ extern "C" ssq_status ssq_icwt_f64(ssq_ctx* ctx, const double* Wx, int64_t ns, i
   SSQ_TRY(ssq_icwt_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, ns, n_cols, wavelet, scales, one_int, x_len, x_mean,
                              flags, (float*)ctx->ws_out.p));
   return download_f32_as_f64(ctx, ctx->ws_out.p, (size_t)x_len, x);
+}
+
+extern "C" ssq_status ssq_cwt_admissibility(int wavelet, double* css) {
+  if (!css) return SSQ_EINVAL;
+  *css = ssqhost::admissibility_ssq(wavelet == SSQ_WAVELET_MORLET);
+  return SSQ_OK;
+}
+
+// issq_cwt: old/ssqueezepy/_ssq_cwt.py:313-378, full inversion; same column sum as icwt.
+extern "C" ssq_status ssq_issq_cwt_batch_f32(ssq_ctx* ctx, const float* d_Tx, int64_t channels, int64_t ns, int64_t n,
+                                             int wavelet, const double* scales, float* d_x) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!d_Tx || !d_x) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  if (!scales) return ssq_fail(ctx, SSQ_EINVAL, "Scales must be provided");
+  if (channels < 1 || ns < 1 || n < 1) return ssq_fail(ctx, SSQ_EINVAL, "issq_cwt: empty Tx");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const double css = ssqhost::admissibility_ssq(wavelet == SSQ_WAVELET_MORLET);
+  const double dj = (ns > 1 && scales[1] > scales[0]) ? std::log(scales[1] / scales[0]) : 0.1;
+  std::vector<float> ones((size_t)ns, 1.f);
+  SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, ones.size() * sizeof(float)));
+  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice));
+  dim3 g((unsigned)((n + 255) / 256), (unsigned)channels);
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  icwt_kernel<<<g, 256, 0, ctx->stream>>>((const float2*)d_Tx, ns, n, n, (const float*)ctx->cwt_scales.p,
+                                          (float)((2.0 / css) * dj), 0.f, d_x);
+  SSQ_TRY(ssq_check_launch(ctx, "icwt_kernel"));
+  ctx->last_kernel = "icwt_kernel";
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_issq_cwt_f64(ssq_ctx* ctx, const double* Tx, int64_t ns, int64_t n, int wavelet,
+                                       const double* scales, double* x) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!Tx || !x) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  if (!scales) return ssq_fail(ctx, SSQ_EINVAL, "Scales must be provided");
+  if (ns < 1 || n < 1) return ssq_fail(ctx, SSQ_EINVAL, "issq_cwt: empty Tx");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t cnt = (size_t)ns * n;
+  SSQ_TRY(upload_f64_as_f32(ctx, Tx, cnt * 2, ctx->ws_in));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, (size_t)n * sizeof(float)));
+  SSQ_TRY(ssq_issq_cwt_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, ns, n, wavelet, scales, (float*)ctx->ws_out.p));
+  return download_f32_as_f64(ctx, ctx->ws_out.p, (size_t)n, x);
 }

@@ -104,4 +104,22 @@ inline int64_t default_scales(int64_t n, int nv, int simd, double* out) {
   return ns;
 }
 
+// Synchrosqueezing admissibility constant of the reference's wavelets (cwt.rs:492-547):
+// Css = integral_0^inf psi-hat(w) / w dw  (old/ssqueezepy/utils/cwt_utils.py:28-47).
+//   gmw (gamma 3, beta 60, unnormalised): 2 int w^59 exp(-w^3) dw = (2/3) Gamma(20) = (2/3) 19!
+//   morlet (mu 6): composite Simpson on [0, 48]; the integrand tends to 6 c exp(-18) at w -> 0.
+inline double admissibility_ssq(bool morlet) {
+  if (!morlet) return (2.0 / 3.0) * std::tgamma(20.0);
+  const double c = std::pow(3.14159265358979323846, -0.25) * std::sqrt(2.0);
+  auto f = [c](double w) {
+    if (w < 1e-8) return c * std::exp(-18.0) * 6.0;
+    return c * (std::exp(-0.5 * (w - 6.0) * (w - 6.0)) - std::exp(-18.0) * std::exp(-0.5 * w * w)) / w;
+  };
+  const int m = 1 << 18;
+  const double h = 48.0 / m;
+  double acc = f(0.0) + f(48.0);
+  for (int i = 1; i < m; ++i) acc += f(i * h) * ((i & 1) ? 4.0 : 2.0);
+  return acc * h / 3.0;
+}
+
 }  // namespace ssqhost

@@ -13,6 +13,11 @@
   ssq_cwt_test.py:19-57,410-419) with the ORACLE's outputs (no reference
   binary exists to produce them): a regression pin, not a reference pin.
 
+* `upstream_adm.npz` -- upstream's synchrosqueezing admissibility constants
+  (`utils/cwt_utils.py:28-47`) for gmw(3, 60) and morlet(6), with upstream's
+  wavelet values at the points that fix the ratio to the Rust wavelets
+  (cwt.rs:492-547 differ from upstream's by a constant factor each).
+
 Neither the GPU tests nor bench.py read /root/reference; they read these files.
 """
 import os
@@ -83,8 +88,21 @@ def readme_cases():
     return out
 
 
+def upstream_adm():
+    from ssqueezepy import Wavelet
+    from ssqueezepy.utils.cwt_utils import adm_ssq
+    out = {}
+    for name, cfg, wpk in (("gmw", {"gamma": 3, "beta": 60}, 20.0 ** (1.0 / 3.0)), ("morlet", {"mu": 6}, 6.0)):
+        wav = Wavelet((name, dict(cfg, dtype="float64")))
+        out[f"{name}_css"] = np.float64(adm_ssq(wav))
+        out[f"{name}_w"] = np.array([0.5 * wpk, wpk, 1.3 * wpk])
+        out[f"{name}_psih"] = np.asarray(wav.fn(out[f"{name}_w"]), dtype=np.float64)
+    return out
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "upstream_adm.npz"), **upstream_adm())
     np.savez_compressed(os.path.join(HERE, "upstream_odd.npz"), **upstream_cases())
     np.savez_compressed(os.path.join(HERE, "readme_cases.npz"), **readme_cases())
-    for f in ("upstream_odd.npz", "readme_cases.npz"):
+    for f in ("upstream_adm.npz", "upstream_odd.npz", "readme_cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -124,3 +124,34 @@ def test_oracle_icwt_formula_and_errors():
         O.icwt(Wx)
     with pytest.raises(IndexError):
         O.icwt(Wx, "gmw", sc, x_len=51)
+
+
+def test_oracle_admissibility_pinned_to_upstream():
+    """adm_ssq of the Rust wavelets (cwt.rs:492-547) = upstream's adm_ssq (utils/cwt_utils.py:28-47) times the
+    constant ratio between the two definitions of the same wavelet (golden: tests/golden/upstream_adm.npz)."""
+    import math
+    z = np.load(os.path.join(G, "upstream_adm.npz"))
+    for wav in ("gmw", "morlet"):
+        w = z[f"{wav}_w"]
+        ratio = O.generate_wavelet_fourier(w, 1.0, wav).real / z[f"{wav}_psih"]
+        assert np.allclose(ratio, ratio[1], rtol=1e-9), (wav, ratio)      # same wavelet up to a constant
+        assert np.isclose(O.adm_ssq(wav), ratio[1] * float(z[f"{wav}_css"]), rtol=2e-6), wav
+    assert np.isclose(O.adm_ssq("gmw"), (2.0 / 3.0) * math.gamma(20.0), rtol=1e-12)  # 2 int w^59 exp(-w^3) dw
+
+
+def test_oracle_cwt_round_trips_with_exact_admissibility():
+    """cwt -> icwt(exact_adm) and ssq_cwt(maximal) -> issq_cwt return x (old/tests/reconstruction_test.py style);
+    with the reference's placeholder constants (cwt.rs:579-583) they do not."""
+    N = 2048
+    t = np.arange(N)
+    x = np.cos(2 * np.pi * 0.05 * t) + 0.5 * np.cos(2 * np.pi * 0.11 * t + 1.0)
+    for wav in ("gmw", "morlet"):
+        Wx, sc, _ = O.cwt(x, wav, nv=32)
+        xr = O.icwt(Wx, wav, sc, exact_adm=True)
+        assert np.abs(xr - x).mean() < 5e-3, wav
+        assert np.abs(O.icwt(Wx, wav, sc) - x).mean() > 0.2, wav
+        Tx, _ = O.ssq_cwt(x, wav, nv=32, maprange="maximal")
+        xs = O.issq_cwt(Tx, wav, sc)
+        assert np.abs(xs - x).mean() < 5e-3, wav
+    with pytest.raises(ValueError):
+        O.issq_cwt(Tx)

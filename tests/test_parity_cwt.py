@@ -210,3 +210,29 @@ def test_icwt_one_integral():
         rs.icwt(Wx, "gmw", sc, x_len=5000)            # index out of bounds in the reference
     with pytest.raises(SsqError):
         rs.icwt(Wx, "gmw", sc, one_int=False)         # two-integral branch not built
+
+
+def test_admissibility_icwt_exact_and_issq_cwt():
+    """the true admissibility constant, icwt with it, and issq_cwt (spec
+    old/ssqueezepy/_ssq_cwt.py:313-378) against the oracle, plus the reconstruction property."""
+    rs = _rs()
+    for wav in ("gmw", "morlet"):
+        assert np.isclose(rs.adm_ssq(wav), O.adm_ssq(wav), rtol=1e-9), wav
+    N = 4096
+    t = np.arange(N)
+    x = np.cos(2 * np.pi * 0.05 * t) + 0.5 * np.cos(2 * np.pi * 0.11 * t + 1.0)
+    for wav in ("gmw", "morlet"):
+        Wx, sc, _ = rs.cwt(x, wav, nv=32)
+        xr = rs.icwt(Wx, wav, sc, exact_adm=True)
+        xo = O.icwt(Wx, wav, sc, exact_adm=True)
+        assert np.abs(xr - xo).max() < RTOL * np.abs(xo).max(), wav
+        assert np.abs(xr - x).mean() < 5e-3, (wav, np.abs(xr - x).mean())
+        Tx, _ = rs.ssq_cwt(x, wav, nv=32, maprange="maximal")
+        xs = rs.issq_cwt(Tx, wav, sc)
+        assert xs.shape == (N,) and xs.dtype == np.float64
+        assert np.abs(xs - O.issq_cwt(Tx, wav, sc)).max() < RTOL * np.abs(x).max(), wav
+        assert np.abs(xs - x).mean() < 5e-3, (wav, np.abs(xs - x).mean())
+    with pytest.raises(ValueError):
+        rs.issq_cwt(Tx)                               # "Scales must be provided"
+    with pytest.raises(TypeError):
+        rs.issq_cwt(Tx.real, "gmw", sc)
