@@ -18,6 +18,16 @@
   wavelet values at the points that fix the ratio to the Rust wavelets
   (cwt.rs:492-547 differ from upstream's by a constant factor each).
 
+* `upstream_even512.npz` -- the BENCHMARK geometry (n_fft=512, hop=32, hann, fs=1): upstream frames the
+  signal one sample earlier than the Rust code for even n_fft (pad n_fft/2 against (n_fft-1)/2,
+  stft_utils.rs:19-49), so upstream run on x[1:] yields, on every frame that touches no padding, exactly
+  the Rust frames of x.  Columns [j0, j1) of upstream's Sx, dSx and Tx are stored.
+* `upstream_cwt.npz` -- upstream `cwt(..., derivative=True)` and `phase_cwt` for an even N whose padded
+  length is the same in both code bases (N=600 -> 1024), explicit scales, l1 norm, reflect padding.
+  The Rust wavelets equal upstream's up to one constant each (`*_ratio`), so Wx/dWx must agree to
+  rounding for gmw; for morlet only where psi-hat is negligible at the Nyquist bin (the Rust grid
+  keeps +pi there, `wavelets/base.rs:18-33`, upstream -pi) -- rows `morlet_rows_ok`.
+
 Neither the GPU tests nor bench.py read /root/reference; they read these files.
 """
 import os
@@ -100,9 +110,53 @@ def upstream_adm():
     return out
 
 
+def upstream_even512():
+    import ssqueezepy as S
+    rng = np.random.default_rng(20261020)
+    N, n_fft, hop = 2560, 512, 32
+    t = np.arange(N)
+    x = rng.standard_normal(N) + 3.0 * np.sin(2 * np.pi * (0.01 + 0.00002 * t) * t)
+    win = np.hanning(n_fft)
+    Tx, Sx, ssqf, Sfs, w, dSx = S.ssq_stft(x[1:], window=win, n_fft=n_fft, hop_len=hop, fs=1.0, modulated=False,
+                                          dtype="float64", get_w=True, get_dWx=True)
+    j0, j1 = (n_fft // 2) // hop + 1, (N - 1 - (n_fft // 2 + 2)) // hop
+    out = dict(x=x, window=win, cols=np.array([j0, j1]), Tx=Tx[:, j0:j1], Sx=Sx[:, j0:j1], dSx=dSx[:, j0:j1],
+               ssq_freqs=np.asarray(ssqf))
+    Tx_o, sf_o, aux = O.ssq_stft(x, win, n_fft=n_fft, hop_len=hop, fs=1.0, return_aux=True)
+    assert np.abs(Tx_o[:, j0:j1] - out["Tx"]).max() <= 1e-12 * np.abs(out["Tx"]).max(), "oracle != upstream"
+    assert np.abs(aux["Sx"][:, j0:j1] - out["Sx"]).max() <= 1e-12 * np.abs(out["Sx"]).max()
+    return out
+
+
+def upstream_cwt():
+    import ssqueezepy as S
+    from ssqueezepy import Wavelet
+    out = {}
+    rng = np.random.default_rng(20261019)
+    N = 600
+    x = rng.standard_normal(N) + np.sin(2 * np.pi * 0.07 * np.arange(N))
+    scales = 2.0 ** np.linspace(1, 6.5, 12)
+    out["x"], out["scales"] = x, scales
+    for name, cfg, wpk in (("gmw", {"gamma": 3, "beta": 60}, 20.0 ** (1.0 / 3.0)), ("morlet", {"mu": 6}, 6.0)):
+        wav = Wavelet((name, dict(cfg, dtype="float64")))
+        Wx, _, dWx = S.cwt(x, wav, scales=scales, fs=1.0, l1_norm=True, derivative=True, padtype="reflect")
+        ratio = float(wav.fn(np.array([wpk]))[0] / O.generate_wavelet_fourier(np.array([wpk]), 1.0, name)[0].real)
+        out[f"{name}_Wx"], out[f"{name}_dWx"], out[f"{name}_ratio"] = Wx, dWx, np.float64(ratio)
+        gamma = 1e-3 * np.abs(Wx).max()
+        out[f"{name}_gamma"] = np.float64(gamma)
+        out[f"{name}_w"] = S.phase_cwt(Wx, dWx, difftype="trig", gamma=gamma)
+        Wo, _, dWo = O.cwt(x, name, scales, fs=1.0, derivative=True)
+        err = np.abs(Wx - ratio * Wo).max(axis=1) / np.abs(Wx).max()
+        out[f"{name}_rows_ok"] = np.nonzero(err < 1e-7)[0]
+        print(name, "rows agreeing with the oracle:", out[f"{name}_rows_ok"], "max err there", err[err < 1e-7].max())
+    return out
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "upstream_even512.npz"), **upstream_even512())
+    np.savez_compressed(os.path.join(HERE, "upstream_cwt.npz"), **upstream_cwt())
     np.savez_compressed(os.path.join(HERE, "upstream_adm.npz"), **upstream_adm())
     np.savez_compressed(os.path.join(HERE, "upstream_odd.npz"), **upstream_cases())
     np.savez_compressed(os.path.join(HERE, "readme_cases.npz"), **readme_cases())
-    for f in ("upstream_adm.npz", "upstream_odd.npz", "readme_cases.npz"):
+    for f in ("upstream_even512.npz", "upstream_cwt.npz", "upstream_adm.npz", "upstream_odd.npz", "readme_cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

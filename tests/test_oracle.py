@@ -155,3 +155,38 @@ def test_oracle_cwt_round_trips_with_exact_admissibility():
         assert np.abs(xs - x).mean() < 5e-3, wav
     with pytest.raises(ValueError):
         O.issq_cwt(Tx)
+
+
+def test_oracle_cwt_pinned_to_upstream():
+    """cwt.rs:169-326 / ssq_cwt.rs:339-435 (padding, xi grid, psi-hat, inverse FFT normalisation, derivative,
+    unpadding) and phase_cwt (ssq_cwt.rs:15-47) against upstream `cwt` / `phase_cwt` outputs
+    (tests/golden/upstream_cwt.npz; the wavelets differ by one constant each, stored as `*_ratio`)."""
+    z = np.load(os.path.join(G, "upstream_cwt.npz"))
+    x, sc = z["x"], z["scales"]
+    for wav, tol in (("gmw", 1e-13), ("morlet", 1e-7)):
+        rows = z[f"{wav}_rows_ok"]
+        assert len(rows) >= 10
+        Wo, _, dWo = O.cwt(x, wav, sc, fs=1.0, derivative=True)
+        r = float(z[f"{wav}_ratio"])
+        Wu, dWu = z[f"{wav}_Wx"], z[f"{wav}_dWx"]
+        assert np.abs(r * Wo[rows] - Wu[rows]).max() < tol * np.abs(Wu).max(), wav
+        assert np.abs(r * dWo[rows] - dWu[rows]).max() < tol * np.abs(dWu).max(), wav
+        # phase transform on upstream's own Wx, dWx: same formula, same gate
+        w = O.phase_cwt(Wu, dWu, float(z[f"{wav}_gamma"]))
+        wu = z[f"{wav}_w"]
+        assert np.array_equal(np.isinf(w), np.isinf(wu)), wav
+        fin = np.isfinite(wu)
+        assert np.allclose(w[fin], wu[fin], rtol=1e-10, atol=1e-14), wav
+
+
+def test_oracle_benchmark_geometry_pinned_to_upstream():
+    """n_fft=512, hop=32 (BASELINE configs[1]): Sx, dSx and Tx of every frame that touches no padding equal
+    upstream's on the one-sample-shifted signal (tests/golden/upstream_even512.npz)."""
+    z = np.load(os.path.join(G, "upstream_even512.npz"))
+    j0, j1 = z["cols"]
+    Tx, sf, aux = O.ssq_stft(z["x"], z["window"], n_fft=512, hop_len=32, fs=1.0, return_aux=True)
+    assert j1 - j0 >= 50
+    for got, key in ((aux["Sx"], "Sx"), (aux["dSx"], "dSx"), (Tx, "Tx")):
+        ref = z[key]
+        assert np.abs(got[:, j0:j1] - ref).max() < 1e-12 * np.abs(ref).max(), key
+    assert np.allclose(sf, z["ssq_freqs"], rtol=0, atol=1e-15)

@@ -29,3 +29,15 @@ def test_c_ref_options():
         To, _ = O.ssq_stft(x, win, n_fft=128, hop_len=16, fs=100.0, **kw)
         assert np.abs(Tx - To).max() < 1e-9 * np.abs(To).max()
     assert cref.num_threads() >= 1
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_c_ref_benchmark_geometry_vs_upstream_golden(mode):
+    """The timed CPU baseline itself against upstream's output at n_fft=512, hop=32 (frames without padding)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "upstream_even512.npz"))
+    j0, j1 = z["cols"]
+    Tx, sf, Sx = cref.ssq_stft(z["x"], z["window"], 512, 32, 1.0, mode=mode, want_Sx=True)
+    assert np.abs(Sx[:, j0:j1] - z["Sx"]).max() < 1e-11 * np.abs(z["Sx"]).max()
+    bad = np.abs(Tx[:, j0:j1] - z["Tx"]) > 1e-9 * np.abs(z["Tx"]).max()
+    assert bad.mean() < 1e-4, bad.mean()

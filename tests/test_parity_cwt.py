@@ -236,3 +236,19 @@ def test_admissibility_icwt_exact_and_issq_cwt():
         rs.issq_cwt(Tx)                               # "Scales must be provided"
     with pytest.raises(TypeError):
         rs.issq_cwt(Tx.real, "gmw", sc)
+
+
+def test_cwt_against_upstream_golden():
+    """The CUDA cwt against upstream ssqueezepy's own output (tests/golden/upstream_cwt.npz): Wx and dWx agree up
+    to the constant ratio between the two wavelet definitions (all gmw rows; morlet rows with no energy at the
+    Nyquist bin)."""
+    rs = _rs()
+    z = np.load(os.path.join(G, "upstream_cwt.npz"))
+    x, sc = z["x"], z["scales"]
+    for wav in ("gmw", "morlet"):
+        rows = z[f"{wav}_rows_ok"]
+        Wx, _, dWx = rs.cwt(x, wav, sc, fs=1.0, derivative=True)
+        r = float(z[f"{wav}_ratio"])
+        Wu, dWu = z[f"{wav}_Wx"], z[f"{wav}_dWx"]
+        assert np.abs(r * Wx[rows] - Wu[rows]).max() < RTOL * np.abs(Wu).max(), wav
+        assert np.abs(r * dWx[rows] - dWu[rows]).max() < RTOL * np.abs(dWu).max(), wav

@@ -136,6 +136,22 @@ def test_ssq_stft_vs_upstream_golden():
         assert np.abs(Tx.sum(0) - To.sum(0)).max() < 1e-3 * np.abs(To).max()
 
 
+def test_benchmark_geometry_vs_upstream_golden():
+    """n_fft=512, hop=32 (the benchmarked kernel) directly against upstream's output on the frames that touch
+    no padding (tests/golden/upstream_even512.npz; see make_golden.py for the one-sample shift)."""
+    z = np.load(os.path.join(G, "upstream_even512.npz"))
+    rs = _rs()
+    j0, j1 = z["cols"]
+    Tx, sf, aux = rs.ssq_stft(z["x"], z["window"], n_fft=512, hop_len=32, fs=1.0, return_aux=True)
+    assert rel(aux["Sx"][:, j0:j1], z["Sx"]) < RTOL
+    assert rel(aux["dSx"][:, j0:j1], z["dSx"]) < 2 * RTOL
+    To = z["Tx"]
+    bad = np.abs(Tx[:, j0:j1] - To) > RTOL * np.abs(To).max()
+    assert bad.mean() < 2e-3, bad.mean()
+    assert np.abs(Tx[:, j0:j1].sum(0) - To.sum(0)).max() < 1e-3 * np.abs(To).max()
+    assert np.allclose(sf, z["ssq_freqs"], rtol=0, atol=1e-15)
+
+
 def test_ssq_stft_options():
     rng = np.random.default_rng(5)
     x = rng.standard_normal(2000)
