@@ -54,6 +54,37 @@ if a.op in ("ssq_cwt", "cwt"):
         print(f"{a.op} ns={ns} iter {it}: {ms:.3f} ms  {a.channels * a.samples / ms / 1e3:.2f} Msamples/s  "
               f"{ab / ms / 1e6:.1f} GB/s algorithmic")
     sys.exit(0)
+if a.op in ("issq_stft", "icwt", "issq_cwt"):
+    # column-sum inverses on random coefficients (timing only): rows x samples complex64 per channel
+    import ctypes as C
+    from ssqueeze_rs_b200._lib import load, raise_status
+    rows = nfq if a.op == "issq_stft" else load().ssq_cwt_default_scales(a.samples, a.nv, 0, C.c_void_p(0))
+    M = torch.randn((a.channels, rows, a.samples, 2), generator=g, device="cuda")
+    y = torch.empty((a.channels, a.samples), dtype=torch.float32, device="cuda")
+    sc = np.ascontiguousarray(2.0 ** (1.0 + np.arange(rows) / a.nv))
+    eng._bind_stream()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(a.iters):
+        ev0.record()
+        if a.op == "issq_stft":
+            eng.issq_stft_ptr(M.data_ptr(), a.channels, rows, a.samples, win, a.n_fft, 1.0, y.data_ptr())
+        elif a.op == "icwt":
+            st = load().ssq_icwt_batch_f32(eng.ctx.handle, M.data_ptr(), a.channels, rows, a.samples, 0,
+                                           sc.ctypes.data, 1, a.samples, 0.0, 0, y.data_ptr())
+            raise_status(st, eng.ctx.handle)
+        else:
+            st = load().ssq_issq_cwt_batch_f32(eng.ctx.handle, M.data_ptr(), a.channels, rows, a.samples, 0,
+                                               sc.ctypes.data, y.data_ptr())
+            raise_status(st, eng.ctx.handle)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        ab = a.channels * (4 * a.samples + 8 * rows * a.samples)
+        print(f"{a.op} rows={rows} iter {it}: {ms:.3f} ms  {a.channels * a.samples / ms / 1e3:.1f} Msamples/s  "
+              f"{ab / ms / 1e6:.1f} GB/s algorithmic")
+    ref = M[0, :, :4096, 0].double().sum(0)
+    print("check", float((y[0, :4096].double() / ref).std()))
+    sys.exit(0)
 if a.op == "istft":
     Sx = torch.empty((a.channels, nfq, nfr), dtype=torch.complex64, device="cuda")
     eng.stft(x, win, a.n_fft, a.hop, out=Sx)
