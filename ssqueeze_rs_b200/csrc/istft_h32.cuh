@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const 
       float2* s = S + lane * AS + warp;
       const bool ok = lane < nf;
 #pragma unroll 8
-      for (int it = 0; it < 32; ++it) {
+      for (int it = 0; it < 32; ++it) {  // (all 32 loads in flight at once measured slower: 11.05 vs 10.43 ms)
         s[8 * it] = ok ? __ldg(g) : make_float2(0.f, 0.f);
         g += gstep;
       }
@@ -246,10 +246,27 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const 
     }
     __syncthreads();
     // ---- transforms: warp w owns frames 4w .. 4w+3 (two packed pairs) --------------------------------
+    // hop == 32: sample lane + 32 j of frame f belongs to the 32-sample block f + j, lane `lane`: the warp
+    // adds its (up to) four frames in a 16-register window and parks 19 finished blocks in its own first
+    // two tile rows (their input has been consumed by then); the gather below then adds <= 5 warp partials
+    // per sample instead of <= 16 frames.
+    float out[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[j] = 0.f;
+    float* wsum = reinterpret_cast<float*>(S + 4 * warp * AS) + lane;  // [19][32] floats (two rows hold 1156)
 #pragma unroll 1
     for (int pr = 0; pr < 2; ++pr) {
       const int fa = 4 * warp + 2 * pr;
-      if (fa >= nf) break;
+      if (fa >= nf) {
+        if (!HOP32 || 4 * warp >= nf) break;
+        // hop 32, second pair absent: its two blocks are just the running window
+        wsum[(2 * pr) * 32] = out[0];
+        wsum[(2 * pr + 1) * 32] = out[1];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) out[j] = out[j + 2];
+        out[14] = out[15] = 0.f;
+        continue;
+      }
       float2* tA = S + fa * AS;
       float2* tB = tA + AS;  // zero row when the frame does not exist
       float2 va[8], vb[8];
@@ -273,16 +290,41 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const 
       }
       __syncwarp();  // both rows fully read before they are overwritten below
       h32_fft512(L, xch, va, vb);  // va[m] = X[lane + 64 m], vb[m] = X[lane + 32 + 64 m]
-      float* yA = reinterpret_cast<float*>(tA);
-      float* yB = reinterpret_cast<float*>(tB);
+      if (HOP32) {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        yA[lane + 64 * m] = va[m].x * war[2 * m];
-        yA[lane + 32 + 64 * m] = vb[m].x * war[2 * m + 1];
-        yB[lane + 64 * m] = -va[m].y * war[2 * m];
-        yB[lane + 32 + 64 * m] = -vb[m].y * war[2 * m + 1];
+        for (int m = 0; m < 8; ++m) {
+          out[2 * m] = fmaf(va[m].x, war[2 * m], out[2 * m]);
+          out[2 * m + 1] = fmaf(vb[m].x, war[2 * m + 1], out[2 * m + 1]);
+        }
+        wsum[(2 * pr) * 32] = out[0];
+#pragma unroll
+        for (int j = 0; j < 15; ++j) out[j] = out[j + 1];
+        out[15] = 0.f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {  // frame B = -Im (a zero row when it does not exist)
+          out[2 * m] = fmaf(-va[m].y, war[2 * m], out[2 * m]);
+          out[2 * m + 1] = fmaf(-vb[m].y, war[2 * m + 1], out[2 * m + 1]);
+        }
+        wsum[(2 * pr + 1) * 32] = out[0];
+#pragma unroll
+        for (int j = 0; j < 15; ++j) out[j] = out[j + 1];
+        out[15] = 0.f;
+      } else {
+        float* yA = reinterpret_cast<float*>(tA);
+        float* yB = reinterpret_cast<float*>(tB);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          yA[lane + 64 * m] = va[m].x * war[2 * m];
+          yA[lane + 32 + 64 * m] = vb[m].x * war[2 * m + 1];
+          yB[lane + 64 * m] = -va[m].y * war[2 * m];
+          yB[lane + 32 + 64 * m] = -vb[m].y * war[2 * m + 1];
+        }
       }
       __syncwarp();
+    }
+    if (HOP32 && 4 * warp < nf) {  // blocks 4 .. 18 of the warp: the window after its fourth frame
+#pragma unroll
+      for (int j = 0; j < 15; ++j) wsum[(4 + j) * 32] = out[j];
     }
     __syncthreads();
     // ---- overlap-add gather over the tile span, one red per padded sample ---------------------------
@@ -292,12 +334,25 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const 
       float* xo = P.xacc + (size_t)ch * P.L + f0 * hop;
       const int64_t room = P.L - f0 * hop;
       const float* Sf = reinterpret_cast<const float*>(S);
-      for (int p = threadIdx.x; p < span; p += blockDim.x) {
-        const int fhi = min(nf - 1, HOP32 ? (p >> 5) : p / hop);
-        const int flo = p < N ? 0 : (HOP32 ? ((p - N + 32) >> 5) : (p - N + hop) / hop);  // ceil((p - N + 1) / hop)
-        float acc = 0.f;
-        for (int f = flo; f <= fhi; ++f) acc += Sf[f * (2 * AS) + (p - hop * f)];
-        if (p < room && flo <= fhi) atomicAdd(xo + p, acc);
+      if (HOP32) {
+        // sample p = 32 B + l of the tile: sum over warps w of wsum_w[B - 4 w][l] = Sf[p + w (4 * 2 AS - 128)]
+        const int wlast = (nf - 1) >> 2;
+        for (int p = threadIdx.x; p < span; p += blockDim.x) {
+          const int B = p >> 5;
+          const int whi = min(wlast, B >> 2);
+          const int wlo = B < 19 ? 0 : (B - 15) >> 2;  // ceil((B - 18) / 4)
+          float acc = 0.f;
+          for (int w = wlo; w <= whi; ++w) acc += Sf[p + w * (8 * AS - 128)];
+          if (p < room) atomicAdd(xo + p, acc);
+        }
+      } else {
+        for (int p = threadIdx.x; p < span; p += blockDim.x) {
+          const int fhi = min(nf - 1, p / hop);
+          const int flo = p < N ? 0 : (p - N + hop) / hop;  // ceil((p - N + 1) / hop)
+          float acc = 0.f;
+          for (int f = flo; f <= fhi; ++f) acc += Sf[f * (2 * AS) + (p - hop * f)];
+          if (p < room && flo <= fhi) atomicAdd(xo + p, acc);
+        }
       }
     }
     __syncthreads();

@@ -483,7 +483,7 @@ def test_istft_512_any_hop(hop, N):
     So = So * (1 + 0.05 * rng.standard_normal(So.shape))
     for wexp in (1, 0):
         xr = rs.istft(So, win, n_fft=512, hop_len=hop, N=N, win_exp=wexp)
-        assert "istft512_tile" in _lib.default_context().last_kernel_name()
+        assert "istft512_" in _lib.default_context().last_kernel_name()
         xo = O.istft(So, win, n_fft=512, hop_len=hop, N=N, win_exp=wexp)
         assert np.abs(xr - xo).max() < RTOL * max(np.abs(xo).max(), 1e-30), (hop, wexp)
 
