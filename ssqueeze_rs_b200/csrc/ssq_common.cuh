@@ -99,11 +99,54 @@ static inline ssq_status ssq_check_launch(ssq_ctx* ctx, const char* what) {
 }
 
 // ---- device helpers -------------------------------------------------------
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// Complex arithmetic on the packed fp32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2): one
+// instruction per complex add, two per complex multiply.  They occupy the fp32 pipe for two
+// cycles, so the flop rate is that of the scalar forms (tools/ubench/fp2.cu: 64 complex adds per
+// clock and SM either way) -- what halves is the number of ISSUE SLOTS, the resource these
+// kernels run out of.  ptxas folds the operand swaps, sign patterns and scalar broadcasts written
+// below into operand modifiers (.LO_HI, .NP, .F32): no MOV is emitted for them.
+typedef unsigned long long ssq_u64;
+__device__ __forceinline__ ssq_u64 pk2(float2 v) {
+  ssq_u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
 }
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 up2(ssq_u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  ssq_u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(r);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  ssq_u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  ssq_u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  ssq_u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+  return up2(r);
+}
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {  // (a.x b.x - a.y b.y, a.y b.x + a.x b.y)
+  return fma2(make_float2(a.y, a.x), make_float2(-b.y, b.y), mul2(a, bc2(b.x)));
+}
+__device__ __forceinline__ float2 cmulcf(float2 a, float2 b) {  // a * conj(b)
+  return fma2(make_float2(a.y, a.x), make_float2(b.y, -b.y), mul2(a, bc2(b.x)));
+}
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return sub2(a, b); }
+__device__ __forceinline__ float2 cmi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+__device__ __forceinline__ float2 cpi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
 
 // Padded-signal sample fetch in the reference's STFT framing
 // (stft_utils.rs:19-65): padded index p, left = (n_fft-1)/2.

@@ -187,7 +187,7 @@ __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2
       const float2 wa = L.tw3a[t - 1];
       va[t] = cmulf(va[t], wa);
       const float2 wb = L.l0 ? w16[t - 1] : wa;
-      vb[t] = make_float2(vb[t].x * wb.x + vb[t].y * wb.y, vb[t].y * wb.x - vb[t].x * wb.y);  // vb * conj(wb)
+      vb[t] = cmulcf(vb[t], wb);  // vb * conj(wb)
     }
     fft8_fwd(va);
     fft8_inv(vb);

@@ -40,19 +40,22 @@ __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, fl
                                               float2 A, float2 B) {
   H32RItem it;
   const unsigned sgn = __float_as_uint(skf) & 0x80000000u;
-  const float c = A.x + B.x, d0 = A.y - B.y;  // 2 Re Sx, +-2 Im Sx
+  const float2 cd = add2(A, make_float2(B.x, -B.y));  // 2 Re Sx, +-2 Im Sx
+  const float c = cd.x, d0 = cd.y;
   if (MODE == 1) {
     const int k = (int)fabsf(skf);
     col[h32r_phys(k)] = make_float2(0.5f * c, __uint_as_float(__float_as_uint(0.5f * d0) ^ sgn));
     if (colB) {
-      const float a = A.y + B.y, b0 = B.x - A.x;
+      const float2 ba = add2(B, make_float2(-A.x, A.y));
+      const float b0 = ba.x, a = ba.y;
       colB[h32r_phys(k)] = make_float2(0.5f * a, __uint_as_float(__float_as_uint(0.5f * b0) ^ sgn));
     }
     it.kb = -1;
     it.vre = it.vim = 0.f;
     return it;
   }
-  const float a = A.y + B.y, b0 = B.x - A.x;  // 2 V (Re with the swap sign)
+  const float2 ba = add2(B, make_float2(-A.x, A.y));  // 2 V (Re with the swap sign)
+  const float b0 = ba.x, a = ba.y;
   const float den = fmaf(c, c, d0 * d0);
   const float num0 = fmaf(b0, c, -a * d0);
   const float q0 = num0 * rcp_approx(den);
@@ -275,11 +278,11 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
         for (int t = 0; t < 8; ++t) {
           const float2 w0 = wtab[lane + 64 * t], w1 = wtab[lane + 32 + 64 * t];
           if (PAIR) {  // real part frame s, imaginary part frame s+1 (same window, samples one position on)
-            va[t] = make_float2(xw[2 * t] * w0.x, xw[2 * t + 1] * w0.x);
-            vb[t] = make_float2(xw[2 * t + 1] * w1.x, xw[2 * t + 2] * w1.x);
+            va[t] = mul2(make_float2(xw[2 * t], xw[2 * t + 1]), bc2(w0.x));
+            vb[t] = mul2(make_float2(xw[2 * t + 1], xw[2 * t + 2]), bc2(w1.x));
           } else {
-            va[t] = make_float2(xw[2 * t] * w0.x, xw[2 * t] * w0.y);
-            vb[t] = make_float2(xw[2 * t + 1] * w1.x, xw[2 * t + 1] * w1.y);
+            va[t] = mul2(bc2(xw[2 * t]), w0);
+            vb[t] = mul2(bc2(xw[2 * t + 1]), w1);
           }
         }
       }
