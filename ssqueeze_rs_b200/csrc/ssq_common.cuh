@@ -116,35 +116,67 @@ __device__ __forceinline__ float2 up2(ssq_u64 v) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
   return r;
 }
+// PK = false selects the scalar forms: the packed ones need aligned register pairs, and a kernel
+// that already sits at its register cap can lose more to the spills than it gains (the stft mode
+// of the n_fft = 512 kernel: 18.5 ms packed with 56 B of spills, 16.8 ms scalar on 384 channels).
+#ifdef SSQ_SCALAR_COMPLEX  // A/B switch for measurements
+#define SSQ_PK_DEFAULT false
+#else
+#define SSQ_PK_DEFAULT true
+#endif
+template <bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  ssq_u64 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
-  return up2(r);
+  if constexpr (PK) {
+    ssq_u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(r);
+  } else {
+    return make_float2(a.x + b.x, a.y + b.y);
+  }
 }
+template <bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
-  ssq_u64 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
-  return up2(r);
+  if constexpr (PK) {
+    ssq_u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(r);
+  } else {
+    return make_float2(a.x - b.x, a.y - b.y);
+  }
 }
+template <bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  ssq_u64 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
-  return up2(r);
+  if constexpr (PK) {
+    ssq_u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(r);
+  } else {
+    return make_float2(a.x * b.x, a.y * b.y);
+  }
 }
+template <bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  ssq_u64 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
-  return up2(r);
+  if constexpr (PK) {
+    ssq_u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+    return up2(r);
+  } else {
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+  }
 }
 __device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+template <bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {  // (a.x b.x - a.y b.y, a.y b.x + a.x b.y)
-  return fma2(make_float2(a.y, a.x), make_float2(-b.y, b.y), mul2(a, bc2(b.x)));
+  return fma2<PK>(make_float2(a.y, a.x), make_float2(-b.y, b.y), mul2<PK>(a, bc2(b.x)));
 }
+template <bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ float2 cmulcf(float2 a, float2 b) {  // a * conj(b)
-  return fma2(make_float2(a.y, a.x), make_float2(b.y, -b.y), mul2(a, bc2(b.x)));
+  return fma2<PK>(make_float2(a.y, a.x), make_float2(b.y, -b.y), mul2<PK>(a, bc2(b.x)));
 }
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return add2(a, b); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return sub2(a, b); }
+template <bool PK = SSQ_PK_DEFAULT>
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return add2<PK>(a, b); }
+template <bool PK = SSQ_PK_DEFAULT>
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return sub2<PK>(a, b); }
 __device__ __forceinline__ float2 cmi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 __device__ __forceinline__ float2 cpi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
 

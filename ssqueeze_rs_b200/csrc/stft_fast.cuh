@@ -28,56 +28,58 @@
 #define SSQ_FAST_ACC_STRIDE 289  // bin k lives at k + (k>>3) (max 288); odd stride -> conflict-free read-out
 #define SSQ_FAST_MAX_HOP 64
 
+template <bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ void fft8_fwd(float2 (&v)[8]) {
   const float S = 0.70710678118654752440f;
-  float2 a0 = caddf(v[0], v[4]), a4 = csubf(v[0], v[4]);
-  float2 a1 = caddf(v[1], v[5]), a5 = csubf(v[1], v[5]);
-  float2 a2 = caddf(v[2], v[6]), a6 = csubf(v[2], v[6]);
-  float2 a3 = caddf(v[3], v[7]), a7 = csubf(v[3], v[7]);
+  float2 a0 = caddf<PK>(v[0], v[4]), a4 = csubf<PK>(v[0], v[4]);
+  float2 a1 = caddf<PK>(v[1], v[5]), a5 = csubf<PK>(v[1], v[5]);
+  float2 a2 = caddf<PK>(v[2], v[6]), a6 = csubf<PK>(v[2], v[6]);
+  float2 a3 = caddf<PK>(v[3], v[7]), a7 = csubf<PK>(v[3], v[7]);
   // odd branch twiddles W8^1, W8^2, W8^3 (the 1/sqrt2 factors are folded into the last layer)
-  float2 p5 = caddf(a5, cmi(a5));  // a5 * (1 - i)      [* S]
+  float2 p5 = caddf<PK>(a5, cmi(a5));  // a5 * (1 - i)      [* S]
   float2 p6 = cmi(a6);             // a6 * (-i)
-  float2 p7 = csubf(cmi(a7), a7);  // a7 * (-1 - i)     [* S]
-  float2 b0 = caddf(a0, a2), b2 = csubf(a0, a2);
-  float2 b1 = caddf(a1, a3), b3 = csubf(a1, a3);
-  float2 b4 = caddf(a4, p6), b6 = csubf(a4, p6);
-  float2 b5 = caddf(p5, p7), b7 = csubf(p5, p7);  // both still lack the factor S
+  float2 p7 = csubf<PK>(cmi(a7), a7);  // a7 * (-1 - i)     [* S]
+  float2 b0 = caddf<PK>(a0, a2), b2 = csubf<PK>(a0, a2);
+  float2 b1 = caddf<PK>(a1, a3), b3 = csubf<PK>(a1, a3);
+  float2 b4 = caddf<PK>(a4, p6), b6 = csubf<PK>(a4, p6);
+  float2 b5 = caddf<PK>(p5, p7), b7 = csubf<PK>(p5, p7);  // both still lack the factor S
   float2 r3 = cmi(b3);                            // -i * b3
   float2 r7 = cmi(b7);                            // -i * b7
-  v[0] = caddf(b0, b1);
-  v[4] = csubf(b0, b1);
-  v[2] = caddf(b2, r3);
-  v[6] = csubf(b2, r3);
-  v[1] = fma2(b5, bc2(S), b4);
-  v[5] = fma2(b5, bc2(-S), b4);
-  v[3] = fma2(r7, bc2(S), b6);
-  v[7] = fma2(r7, bc2(-S), b6);
+  v[0] = caddf<PK>(b0, b1);
+  v[4] = csubf<PK>(b0, b1);
+  v[2] = caddf<PK>(b2, r3);
+  v[6] = csubf<PK>(b2, r3);
+  v[1] = fma2<PK>(b5, bc2(S), b4);
+  v[5] = fma2<PK>(b5, bc2(-S), b4);
+  v[3] = fma2<PK>(r7, bc2(S), b6);
+  v[7] = fma2<PK>(r7, bc2(-S), b6);
 }
 
 // Same butterfly with the conjugate kernel: v[m] <- sum_t v[t] W_8^{-t m}.
+template <bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ void fft8_inv(float2 (&v)[8]) {
   const float S = 0.70710678118654752440f;
-  float2 a0 = caddf(v[0], v[4]), a4 = csubf(v[0], v[4]);
-  float2 a1 = caddf(v[1], v[5]), a5 = csubf(v[1], v[5]);
-  float2 a2 = caddf(v[2], v[6]), a6 = csubf(v[2], v[6]);
-  float2 a3 = caddf(v[3], v[7]), a7 = csubf(v[3], v[7]);
-  float2 p5 = caddf(a5, cpi(a5));  // a5 * (1 + i)      [* S]
+  float2 a0 = caddf<PK>(v[0], v[4]), a4 = csubf<PK>(v[0], v[4]);
+  float2 a1 = caddf<PK>(v[1], v[5]), a5 = csubf<PK>(v[1], v[5]);
+  float2 a2 = caddf<PK>(v[2], v[6]), a6 = csubf<PK>(v[2], v[6]);
+  float2 a3 = caddf<PK>(v[3], v[7]), a7 = csubf<PK>(v[3], v[7]);
+  float2 p5 = caddf<PK>(a5, cpi(a5));  // a5 * (1 + i)      [* S]
   float2 p6 = cpi(a6);             // a6 * (+i)
-  float2 p7 = csubf(cpi(a7), a7);  // a7 * (-1 + i)     [* S]
-  float2 b0 = caddf(a0, a2), b2 = csubf(a0, a2);
-  float2 b1 = caddf(a1, a3), b3 = csubf(a1, a3);
-  float2 b4 = caddf(a4, p6), b6 = csubf(a4, p6);
-  float2 b5 = caddf(p5, p7), b7 = csubf(p5, p7);
+  float2 p7 = csubf<PK>(cpi(a7), a7);  // a7 * (-1 + i)     [* S]
+  float2 b0 = caddf<PK>(a0, a2), b2 = csubf<PK>(a0, a2);
+  float2 b1 = caddf<PK>(a1, a3), b3 = csubf<PK>(a1, a3);
+  float2 b4 = caddf<PK>(a4, p6), b6 = csubf<PK>(a4, p6);
+  float2 b5 = caddf<PK>(p5, p7), b7 = csubf<PK>(p5, p7);
   float2 r3 = cpi(b3);  // +i * b3
   float2 r7 = cpi(b7);  // +i * b7
-  v[0] = caddf(b0, b1);
-  v[4] = csubf(b0, b1);
-  v[2] = caddf(b2, r3);
-  v[6] = csubf(b2, r3);
-  v[1] = fma2(b5, bc2(S), b4);
-  v[5] = fma2(b5, bc2(-S), b4);
-  v[3] = fma2(r7, bc2(S), b6);
-  v[7] = fma2(r7, bc2(-S), b6);
+  v[0] = caddf<PK>(b0, b1);
+  v[4] = csubf<PK>(b0, b1);
+  v[2] = caddf<PK>(b2, r3);
+  v[6] = csubf<PK>(b2, r3);
+  v[1] = fma2<PK>(b5, bc2(S), b4);
+  v[5] = fma2<PK>(b5, bc2(-S), b4);
+  v[3] = fma2<PK>(r7, bc2(S), b6);
+  v[7] = fma2<PK>(r7, bc2(-S), b6);
 }
 
 // Bin k of a frame's accumulator column lives at k + (k >> 3): one pad slot per 8

@@ -120,11 +120,11 @@ struct H32Lane {
 // ROT: the last butterfly of vb uses the conjugate kernel (see stft_h32r.cuh).
 // TW2POW: stage-2 twiddles by powers of one table entry (saves 12 shared-memory wavefronts, costs 24
 // multiplies: a gain where the data pipe binds -- stft/ssq_stft -- and a loss for istft).
-template <bool ROT = false, bool TW2POW = ROT>
+template <bool ROT = false, bool TW2POW = ROT, bool PK = SSQ_PK_DEFAULT>
 __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2 (&va)[8], float2 (&vb)[8]) {
   const int lane = L.lane, j2 = L.j2;
-  fft8_fwd(va);
-  fft8_fwd(vb);
+  fft8_fwd<PK>(va);
+  fft8_fwd<PK>(vb);
   {
     float4* rowa = reinterpret_cast<float4*>(xch + lane * 8);
     float4* rowb = reinterpret_cast<float4*>(xch + (lane + 32) * 8);
@@ -146,24 +146,24 @@ __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2
     float2 w[8];
     w[1] = L.tw2[1];  // W_64^{r t}, r = lane & 7
     if (TW2POW) {     // the other powers by products at most 3 deep
-      w[2] = cmulf(w[1], w[1]);
-      w[3] = cmulf(w[2], w[1]);
-      w[4] = cmulf(w[2], w[2]);
-      w[5] = cmulf(w[4], w[1]);
-      w[6] = cmulf(w[4], w[2]);
-      w[7] = cmulf(w[4], w[3]);
+      w[2] = cmulf<PK>(w[1], w[1]);
+      w[3] = cmulf<PK>(w[2], w[1]);
+      w[4] = cmulf<PK>(w[2], w[2]);
+      w[5] = cmulf<PK>(w[4], w[1]);
+      w[6] = cmulf<PK>(w[4], w[2]);
+      w[7] = cmulf<PK>(w[4], w[3]);
     } else {
 #pragma unroll
       for (int t = 2; t < 8; ++t) w[t] = L.tw2[t];
     }
 #pragma unroll
     for (int t = 1; t < 8; ++t) {
-      va[t] = cmulf(va[t], w[t]);
-      vb[t] = cmulf(vb[t], w[t]);
+      va[t] = cmulf<PK>(va[t], w[t]);
+      vb[t] = cmulf<PK>(vb[t], w[t]);
     }
   }
-  fft8_fwd(va);
-  fft8_fwd(vb);
+  fft8_fwd<PK>(va);
+  fft8_fwd<PK>(vb);
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     xch[L.wr2 + 8 * (t ^ L.g2)] = va[t];
@@ -185,21 +185,21 @@ __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2
 #pragma unroll
     for (int t = 1; t < 8; ++t) {
       const float2 wa = L.tw3a[t - 1];
-      va[t] = cmulf(va[t], wa);
+      va[t] = cmulf<PK>(va[t], wa);
       const float2 wb = L.l0 ? w16[t - 1] : wa;
-      vb[t] = cmulcf(vb[t], wb);  // vb * conj(wb)
+      vb[t] = cmulcf<PK>(vb[t], wb);  // vb * conj(wb)
     }
-    fft8_fwd(va);
-    fft8_inv(vb);
+    fft8_fwd<PK>(va);
+    fft8_inv<PK>(vb);
     return;
   }
 #pragma unroll
   for (int t = 1; t < 8; ++t) {
-    va[t] = cmulf(va[t], L.tw3a[t - 1]);
-    vb[t] = cmulf(vb[t], L.tw3b[t - 1]);
+    va[t] = cmulf<PK>(va[t], L.tw3a[t - 1]);
+    vb[t] = cmulf<PK>(vb[t], L.tw3b[t - 1]);
   }
-  fft8_fwd(va);  // va[m] = Z[lane + 64 m]
-  fft8_fwd(vb);  // vb[m] = Z[j2 + 64 m]
+  fft8_fwd<PK>(va);  // va[m] = Z[lane + 64 m]
+  fft8_fwd<PK>(vb);  // vb[m] = Z[j2 + 64 m]
 }
 
 template <int MODE, int SQZ>

@@ -40,13 +40,13 @@ __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, fl
                                               float2 A, float2 B) {
   H32RItem it;
   const unsigned sgn = __float_as_uint(skf) & 0x80000000u;
-  const float2 cd = add2(A, make_float2(B.x, -B.y));  // 2 Re Sx, +-2 Im Sx
+  const float2 cd = add2<MODE == 0>(A, make_float2(B.x, -B.y));  // 2 Re Sx, +-2 Im Sx
   const float c = cd.x, d0 = cd.y;
   if (MODE == 1) {
     const int k = (int)fabsf(skf);
     col[h32r_phys(k)] = make_float2(0.5f * c, __uint_as_float(__float_as_uint(0.5f * d0) ^ sgn));
     if (colB) {
-      const float2 ba = add2(B, make_float2(-A.x, A.y));
+      const float2 ba = add2<MODE == 0>(B, make_float2(-A.x, A.y));
       const float b0 = ba.x, a = ba.y;
       colB[h32r_phys(k)] = make_float2(0.5f * a, __uint_as_float(__float_as_uint(0.5f * b0) ^ sgn));
     }
@@ -54,7 +54,7 @@ __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, fl
     it.vre = it.vim = 0.f;
     return it;
   }
-  const float2 ba = add2(B, make_float2(-A.x, A.y));  // 2 V (Re with the swap sign)
+  const float2 ba = add2<MODE == 0>(B, make_float2(-A.x, A.y));  // 2 V (Re with the swap sign)
   const float b0 = ba.x, a = ba.y;
   const float den = fmaf(c, c, d0 * d0);
   const float num0 = fmaf(b0, c, -a * d0);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
   const bool l0 = L.l0;
   unsigned char* tagA = reinterpret_cast<unsigned char*>(xch);  // tags alias the exchange buffer
   unsigned char* tagB = tagA + 264;
-  h32_fft512<true>(L, xch, va, vb);
+  h32_fft512<true, true, MODE == 0>(L, xch, va, vb);
   __syncwarp();  // stage-3 reads done before the tags overwrite the buffer
 
   // pair of step r: lanes >= 1 (va[r], vb[r]); lane 0: r < 4: (va[r], va[(8-r)&7]), r >= 4: (vb[11-r], vb[r-4])
@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
         for (int t = 0; t < 8; ++t) {
           const float2 w0 = wtab[lane + 64 * t], w1 = wtab[lane + 32 + 64 * t];
           if (PAIR) {  // real part frame s, imaginary part frame s+1 (same window, samples one position on)
-            va[t] = mul2(make_float2(xw[2 * t], xw[2 * t + 1]), bc2(w0.x));
-            vb[t] = mul2(make_float2(xw[2 * t + 1], xw[2 * t + 2]), bc2(w1.x));
+            va[t] = mul2<false>(make_float2(xw[2 * t], xw[2 * t + 1]), bc2(w0.x));
+            vb[t] = mul2<false>(make_float2(xw[2 * t + 1], xw[2 * t + 2]), bc2(w1.x));
           } else {
             va[t] = mul2(bc2(xw[2 * t]), w0);
             vb[t] = mul2(bc2(xw[2 * t + 1]), w1);
