@@ -290,6 +290,60 @@ def test_fast_path_512(hop, N):
         _flip_tolerant_compare(Tx, To, max_bad_frac=4e-3)
 
 
+@pytest.mark.parametrize("hop,N", [(256, 40000), (100, 9000), (1024, 30000), (1, 1500), (32, 300)])
+def test_fast_path_1024(hop, N):
+    """n_fft=1024 register-FFT kernel (tests/stft_ssq_test.py:166-167: the reference's multichannel script uses
+    n_fft=1024, hop_length=256): ssq / stft, options, a tonal signal (collision path), batched, modulated."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    rng = np.random.default_rng(hop)
+    x = rng.standard_normal(N) * 30.0
+    win = np.hanning(1024)
+    fs = 30000.0
+    Tx, sf = rs.ssq_stft(x, win, n_fft=1024, hop_len=hop, fs=fs)
+    assert "1024" in _lib.default_context().last_kernel_name()
+    To, sfo = O.ssq_stft(x, win, n_fft=1024, hop_len=hop, fs=fs)
+    assert np.allclose(sf, sfo, rtol=1e-15, atol=0)
+    _flip_tolerant_compare(Tx, To)
+    Sx, _ = rs.stft(x, 1024, hop, win, "reflect")
+    assert "1024" in _lib.default_context().last_kernel_name()
+    So, _ = O.stft(x, 1024, hop, win, "reflect")
+    assert rel(Sx, So) < RTOL
+    for kw in (dict(padtype="zero"), dict(squeezing="lebesgue"), dict(gamma=40.0), dict(modulated=True)):
+        Tx, _ = rs.ssq_stft(x, win, n_fft=1024, hop_len=hop, fs=fs, **kw)
+        To, _ = O.ssq_stft(x, win, n_fft=1024, hop_len=hop, fs=fs, **kw)
+        _flip_tolerant_compare(Tx, To, max_bad_frac=4e-3)
+    # tonal: every bin of a frame is squeezed into a few destination bins
+    t = np.arange(N) / fs
+    xt = np.sin(2 * np.pi * 1234.5 * t) + 0.3 * np.sin(2 * np.pi * 5000.0 * t)
+    Tx, _ = rs.ssq_stft(xt, win, n_fft=1024, hop_len=hop, fs=fs)
+    To, _ = O.ssq_stft(xt, win, n_fft=1024, hop_len=hop, fs=fs)
+    _flip_tolerant_compare(Tx, To, max_bad_frac=1e-2)
+    # run-to-run identical
+    Tx2, _ = rs.ssq_stft(xt, win, n_fft=1024, hop_len=hop, fs=fs)
+    assert np.array_equal(Tx, Tx2)
+
+
+def test_fast_path_1024_batched_matches_generic():
+    import torch
+    from ssqueeze_rs_b200.batch import Engine
+    eng = Engine(0)
+    rng = np.random.default_rng(11)
+    ch, n = 7, 70001
+    x = torch.from_numpy((rng.standard_normal((ch, n)) * 10).astype(np.float32)).cuda()
+    win = np.hanning(1024)
+    a = eng.ssq_stft(x, win, n_fft=1024, hop_len=256, fs=1000.0).cpu().numpy()
+    assert "1024" in eng.last_kernel_name()
+    os.environ["SSQ_NO_R1024"] = "1"
+    try:
+        b = eng.ssq_stft(x, win, n_fft=1024, hop_len=256, fs=1000.0).cpu().numpy()
+        assert "generic" in eng.last_kernel_name()
+    finally:
+        del os.environ["SSQ_NO_R1024"]
+    for c in range(ch):
+        _flip_tolerant_compare(a[c].astype(np.complex128), b[c].astype(np.complex128), max_bad_frac=4e-3)
+
+
 def test_batched_device_api_matches_per_channel():
     import torch
     from ssqueeze_rs_b200.batch import Engine
