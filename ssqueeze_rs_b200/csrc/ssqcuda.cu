@@ -160,6 +160,7 @@ struct StftTables {
   const float2* tw;
   const float* wa;
   const float* wpow;
+  const float2* wpair;  // (win, dwin * s) interleaved; not for TAB_ISTFT (shares the slots of wa / wpow)
   double s_scale;
 };
 
@@ -192,6 +193,12 @@ static ssq_status stft_tables(ssq_ctx* ctx, const std::vector<double>& wfit, int
       h[(size_t)2 * N + 2 * i] = (float)std::cos(ang);
       h[(size_t)2 * N + 2 * i + 1] = (float)std::sin(ang);
     }
+    if (kind != TAB_ISTFT) {
+      for (int i = 0; i < N; ++i) {
+        h[(size_t)4 * N + 2 * i] = h[i];
+        h[(size_t)4 * N + 2 * i + 1] = h[(size_t)N + i];
+      }
+    }
     if (kind == TAB_ISTFT) {
       for (int i = 0; i < N; ++i) {
         const double wa = win_exp == 0 ? 1.0 : std::pow(wfit[i], (double)win_exp);
@@ -214,6 +221,7 @@ static ssq_status stft_tables(ssq_ctx* ctx, const std::vector<double>& wfit, int
   T->tw = (const float2*)(base + 2 * (size_t)N);
   T->wa = base + 4 * (size_t)N;
   T->wpow = base + 5 * (size_t)N;
+  T->wpair = (const float2*)(base + 4 * (size_t)N);
   T->s_scale = ctx->tab_sscale;
   return SSQ_OK;
 }
@@ -321,6 +329,7 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   P.padtype = c.padtype == SSQ_PAD_ZERO ? SSQ_PAD_ZERO : SSQ_PAD_REFLECT;
   P.win = T.win;
   P.dwin = T.dwin;
+  P.wpair = T.wpair;
   P.tw = T.tw;
   const double dw_f = 0.5 * c.fs / ((double)n_freqs - 1.0);  // ssq_stft.rs:50,273
   const double gamma = (c.gamma >= 0.0) ? c.gamma : 10.0 * kEps64;  // NaN compares false -> default

@@ -29,6 +29,7 @@ struct StftParams {
   int left, padtype;
   const float* win;     // [n_fft]
   const float* dwin;    // [n_fft] diff window * s_scale (all zero in stft mode)
+  const float2* wpair;  // [n_fft] (win, dwin) interleaved
   const float2* tw;     // [n_fft] exp(-2 pi i j / n_fft)
   float cphase;         // (n_freqs-1)/(pi*s_scale)
   float gate2;          // (2*gamma)^2 : compare with |2 Sx|^2

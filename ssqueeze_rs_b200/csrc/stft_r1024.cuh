@@ -98,9 +98,9 @@ __device__ __forceinline__ R1KItem r1k_item(const StftParams& P, float txs, floa
   const float num = fmaf(b, c, -a * d);
   const float q = num * rcp_approx(den);
   const float binf = fabsf(fmaf(-q, P.cphase, kf));
-  const float r = ceilf(binf - 0.5f);
-  it.kb = (int)fminf(fmaxf(r, 0.f), 512.f);  // fmaxf(NaN, 0) = 0 -> bin 0 like the reference
-  if (den < P.gate2) it.kb = -1;              // |Sx| < gamma (ssq_stft.rs:23): dropped
+  // nearest grid point, ties to the lower index, clamped; NaN converts to 0 -> bin 0 like the reference
+  it.kb = min(max(__float2int_ru(binf - 0.5f), 0), 512);
+  if (den < P.gate2) it.kb = -1;  // |Sx| < gamma (ssq_stft.rs:23): dropped
   if (SQZ == SSQ_SQUEEZE_LEBESGUE) {
     it.vre = P.leb_val;
     it.vim = 0.f;
@@ -192,8 +192,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
           for (int t = 0; t < 32; ++t) xs[t] = h32r_edge_sample(xc, P.n, p0 + 32 * t, P.left, P.padtype, P.x_origin);
         }
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
-          v[t] = mul2<PK>(bc2(xs[t]), make_float2(__ldg(P.win + lane + 32 * t), __ldg(P.dwin + lane + 32 * t)));
+        for (int t = 0; t < 32; ++t) v[t] = mul2<PK>(bc2(xs[t]), __ldg(P.wpair + lane + 32 * t));
       }
       r1k_fft32<PK>(v);  // v[R1K_REG(kappa)] = Y[lane][kappa]
 #pragma unroll
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
         }
         if (cur.kb >= 0) tagA[cur.kb] = (unsigned char)lane;
         __syncwarp();
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < 17; ++i) {
           R1KItem nxt;
           nxt.kb = -1;
@@ -275,7 +274,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
           } else {
             r1k_collision(col, T, cur.kb, cur.vre, cur.vim, mine, lane);
           }
-          if (nxt.kb >= 0) Tn[nxt.kb] = (unsigned char)lane;
+          if (i < 16 && nxt.kb >= 0) Tn[nxt.kb] = (unsigned char)lane;
           __syncwarp();
           cur = nxt;
         }
