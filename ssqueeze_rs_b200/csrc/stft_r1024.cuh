@@ -83,12 +83,13 @@ struct R1KItem {
 
 // A = Z[k], B = Z[1024 - k] -> item of source bin k (kf = (float)k).
 template <int MODE, int SQZ>
-__device__ __forceinline__ R1KItem r1k_item(const StftParams& P, float txs, float2* col, int k, float kf, float2 A,
-                                            float2 B) {
+__device__ __forceinline__ R1KItem r1k_item(const StftParams& P, float txs, float2* col, float2* colB, int k,
+                                            float kf, float2 A, float2 B) {
   R1KItem it;
   const float c = A.x + B.x, d = A.y - B.y;  // 2 Sx
   if (MODE == 1) {
     col[k] = make_float2(0.5f * c, 0.5f * d);
+    if (colB) colB[k] = make_float2(0.5f * (A.y + B.y), 0.5f * (B.x - A.x));  // second frame of the packed pair
     it.kb = -1;
     it.vre = it.vim = 0.f;
     return it;
@@ -149,7 +150,7 @@ template <int MODE, int SQZ, int NW, int F>
 __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftParams P) {
   constexpr int N = 1024, AS = R1K_AS, XS = R1K_XS, FPW = F / NW;
   constexpr bool PK = SSQ_PK_DEFAULT;
-  static_assert(F % NW == 0, "frames per tile must split evenly over the warps");
+  static_assert(F % NW == 0 && (F / NW) % 2 == 0, "frames per warp: even (stft mode packs pairs)");
   extern __shared__ float2 smem[];
   float2* acc = smem;  // [F][AS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -174,11 +175,14 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
     const int64_t tf0 = (int64_t)(tile - ch * tpc) * F;
     const int nf = (int)min((int64_t)F, P.n_frames - tf0);
     const float* xc = P.x + (size_t)ch * P.x_stride;
+    // stft mode: two frames per FFT (z = x_A w + i x_B w; the "V" half of the split is frame B's spectrum)
+    constexpr int STEP = (MODE == 1) ? 2 : 1;
 #pragma unroll 1
-    for (int s = 0; s < FPW; ++s) {
+    for (int s = 0; s < FPW; s += STEP) {
       const int fl = warp * FPW + s;
       if (fl >= nf) break;
       float2* col = acc + fl * AS;
+      float2* colB = (MODE == 1 && fl + 1 < nf) ? col + AS : nullptr;
       float2 v[32];
       {
         const int64_t p0 = (P.frame0 + tf0 + fl) * (int64_t)P.hop + lane;  // padded position of t = 0
@@ -191,8 +195,26 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
 #pragma unroll
           for (int t = 0; t < 32; ++t) xs[t] = h32r_edge_sample(xc, P.n, p0 + 32 * t, P.left, P.padtype, P.x_origin);
         }
+        if (MODE == 1) {
+          float xb[32];
+          const int64_t p1 = p0 + P.hop;
+          if (!colB) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = mul2<PK>(bc2(xs[t]), __ldg(P.wpair + lane + 32 * t));
+            for (int t = 0; t < 32; ++t) xb[t] = 0.f;
+          } else if (p1 - lane - P.left >= 0 && p1 - lane + N - 1 - P.left < P.n) {
+            const float* xp = xc + (p1 - lo);
+#pragma unroll
+            for (int t = 0; t < 32; ++t) xb[t] = __ldg(xp + 32 * t);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) xb[t] = h32r_edge_sample(xc, P.n, p1 + 32 * t, P.left, P.padtype, P.x_origin);
+          }
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = mul2<PK>(make_float2(xs[t], xb[t]), bc2(__ldg(P.win + lane + 32 * t)));
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = mul2<PK>(bc2(xs[t]), __ldg(P.wpair + lane + 32 * t));
+        }
       }
       r1k_fft32<PK>(v);  // v[R1K_REG(kappa)] = Y[lane][kappa]
 #pragma unroll
@@ -226,14 +248,14 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
         float2 B = make_float2(__shfl_sync(0xffffffffu, Bs.x, partner), __shfl_sync(0xffffffffu, Bs.y, partner));
         if (l0) B = v[R1K_REG((32 - m) & 31)];  // lane 0 pairs with itself: Z[1024 - 32 m]
         const int k = lane + 32 * m;
-        const R1KItem it = r1k_item<MODE, SQZ>(P, txs, col, k, (float)k, A, B);
+        const R1KItem it = r1k_item<MODE, SQZ>(P, txs, col, colB, k, (float)k, A, B);
         if (MODE == 0) {
           sval[k] = make_float2(it.vre, it.vim);
           skey[k] = it.kb;
         }
       }
       if (l0) {
-        const R1KItem it = r1k_item<MODE, SQZ>(P, txs, col, 512, 512.f, v[R1K_REG(16)], v[R1K_REG(16)]);
+        const R1KItem it = r1k_item<MODE, SQZ>(P, txs, col, colB, 512, 512.f, v[R1K_REG(16)], v[R1K_REG(16)]);
         if (MODE == 0) {
           sval[512] = make_float2(it.vre, it.vim);
           skey[512] = it.kb;
