@@ -8,6 +8,7 @@
 #include "stft_h32.cuh"
 #include "stft_h32r.cuh"
 #include "stft_r1024.cuh"
+#include "stft_r256.cuh"
 #include "istft_h32.cuh"
 #include "cwt_kernels.cuh"
 
@@ -355,6 +356,10 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
     if (st != SSQ_OK) return st;
     if (!done) {
       st = stft_r1024_launch(ctx, P, &done);
+      if (st != SSQ_OK) return st;
+    }
+    if (!done) {
+      st = stft_r256_launch(ctx, P, &done);
       if (st != SSQ_OK) return st;
     }
     if (!done && !streaming) {  // the older kernels do not take a frame offset

@@ -82,7 +82,7 @@ struct R1KItem {
 };
 
 // A = Z[k], B = Z[1024 - k] -> item of source bin k (kf = (float)k).
-template <int MODE, int SQZ>
+template <int MODE, int SQZ, int KMAX = 512>
 __device__ __forceinline__ R1KItem r1k_item(const StftParams& P, float txs, float2* col, float2* colB, int k,
                                             float kf, float2 A, float2 B) {
   R1KItem it;
@@ -100,7 +100,7 @@ __device__ __forceinline__ R1KItem r1k_item(const StftParams& P, float txs, floa
   const float q = num * rcp_approx(den);
   const float binf = fabsf(fmaf(-q, P.cphase, kf));
   // nearest grid point, ties to the lower index, clamped; NaN converts to 0 -> bin 0 like the reference
-  it.kb = min(max(__float2int_ru(binf - 0.5f), 0), 512);
+  it.kb = min(max(__float2int_ru(binf - 0.5f), 0), KMAX);
   if (den < P.gate2) it.kb = -1;  // |Sx| < gamma (ssq_stft.rs:23): dropped
   if (SQZ == SSQ_SQUEEZE_LEBESGUE) {
     it.vre = P.leb_val;

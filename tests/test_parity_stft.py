@@ -324,6 +324,57 @@ def test_fast_path_1024(hop, N):
     assert np.array_equal(Tx, Tx2)
 
 
+@pytest.mark.parametrize("hop,N", [(64, 1000), (64, 40000), (17, 5000), (300, 30000), (1, 900), (8, 100)])
+def test_fast_path_256(hop, N):
+    """n_fft=256 register-FFT kernel, four frames per warp (README / tests/stft_test.py:137-151: n_fft=256, hop 64)."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    rng = np.random.default_rng(hop + 1)
+    x = rng.standard_normal(N) * 30.0
+    win = np.hanning(256)
+    fs = 1000.0
+    Tx, sf = rs.ssq_stft(x, win, n_fft=256, hop_len=hop, fs=fs)
+    assert "256" in _lib.default_context().last_kernel_name()
+    To, sfo = O.ssq_stft(x, win, n_fft=256, hop_len=hop, fs=fs)
+    assert np.allclose(sf, sfo, rtol=1e-15, atol=0)
+    _flip_tolerant_compare(Tx, To)
+    Sx, _ = rs.stft(x, 256, hop, win, "reflect")
+    assert "256" in _lib.default_context().last_kernel_name()
+    So, _ = O.stft(x, 256, hop, win, "reflect")
+    assert rel(Sx, So) < RTOL
+    for kw in (dict(padtype="zero"), dict(squeezing="lebesgue"), dict(gamma=40.0), dict(modulated=True)):
+        Tx, _ = rs.ssq_stft(x, win, n_fft=256, hop_len=hop, fs=fs, **kw)
+        To, _ = O.ssq_stft(x, win, n_fft=256, hop_len=hop, fs=fs, **kw)
+        _flip_tolerant_compare(Tx, To, max_bad_frac=4e-3)
+    t = np.arange(N) / fs
+    xt = np.sin(2 * np.pi * 100.0 * t) + 0.3 * np.sin(2 * np.pi * 333.3 * t)  # README sine plus one
+    Tx, _ = rs.ssq_stft(xt, win, n_fft=256, hop_len=hop, fs=fs)
+    To, _ = O.ssq_stft(xt, win, n_fft=256, hop_len=hop, fs=fs)
+    _flip_tolerant_compare(Tx, To, max_bad_frac=1e-2)
+    Tx2, _ = rs.ssq_stft(xt, win, n_fft=256, hop_len=hop, fs=fs)
+    assert np.array_equal(Tx, Tx2)
+
+
+def test_fast_path_256_batched_matches_generic():
+    import torch
+    from ssqueeze_rs_b200.batch import Engine
+    eng = Engine(0)
+    rng = np.random.default_rng(12)
+    ch, n = 9, 33333
+    x = torch.from_numpy((rng.standard_normal((ch, n)) * 10).astype(np.float32)).cuda()
+    win = np.hanning(256)
+    a = eng.ssq_stft(x, win, n_fft=256, hop_len=64, fs=1000.0).cpu().numpy()
+    assert "256" in eng.last_kernel_name()
+    os.environ["SSQ_NO_R256"] = "1"
+    try:
+        b = eng.ssq_stft(x, win, n_fft=256, hop_len=64, fs=1000.0).cpu().numpy()
+        assert "generic" in eng.last_kernel_name()
+    finally:
+        del os.environ["SSQ_NO_R256"]
+    for c in range(ch):
+        _flip_tolerant_compare(a[c].astype(np.complex128), b[c].astype(np.complex128), max_bad_frac=4e-3)
+
+
 def test_fast_path_1024_batched_matches_generic():
     import torch
     from ssqueeze_rs_b200.batch import Engine

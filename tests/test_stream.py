@@ -51,7 +51,8 @@ def test_stream_short_recordings_and_options():
     _run(33, 1, [5], 512, 32, "f32")
 
 
-def test_stream_generic_kernel_other_hops():
-    assert "generic" in _run(9000, 4, [2500, 777], 256, 64, "f32")
+def test_stream_other_kernels_and_hops():
+    assert "256" in _run(9000, 4, [2500, 777], 256, 64, "f32")        # four frames per warp
+    assert "1024" in _run(20000, 3, [4100, 999], 1024, 256, "i16")
     _run(6000, 2, [1700], 512, 300, "i16")              # hop > n_fft/2: end-reflection reaches before the frame start
-    _run(4000, 2, [1111], 128, 1, "f32")
+    assert "generic" in _run(4000, 2, [1111], 128, 1, "f32")
