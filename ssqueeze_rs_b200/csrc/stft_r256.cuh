@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft256_kernel(const StftParam
   constexpr int N = 256, AS = R256_AS, XS = R1K_XS, SS = R256_SS, GPW = F / (4 * NW);
   constexpr bool PK = SSQ_PK_DEFAULT;
   static_assert(F % (4 * NW) == 0, "a warp takes its frames four at a time");
+  // stft mode: two groups per FFT (z = x_A w + i x_B w, frame B = frame A + 4)
+  constexpr int STEP = (MODE == 1) ? 2 : 1;
+  static_assert(GPW % STEP == 0, "stft mode packs pairs of groups");
   extern __shared__ float2 smem[];
   float2* acc = smem;  // [F][AS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -82,12 +85,13 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft256_kernel(const StftParam
     const int nf = (int)min((int64_t)F, P.n_frames - tf0);
     const float* xc = P.x + (size_t)ch * P.x_stride;
 #pragma unroll 1
-    for (int s = 0; s < GPW; ++s) {
+    for (int s = 0; s < GPW; s += STEP) {
       const int fl0 = (warp * GPW + s) * 4;
       if (fl0 >= nf) break;
       const int fl = fl0 + g;
       const bool live = fl < nf;  // frames past the end compute on zeros; their columns are never stored
       float2* col = acc + fl * AS;
+      float2* colB = (MODE == 1) ? col + 4 * AS : nullptr;  // (a column past nf is written but never stored)
       float2 v[32];
       {
         const int64_t p0 = (P.frame0 + tf0 + fl) * (int64_t)P.hop + c;  // padded position of t = 0
@@ -103,8 +107,26 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft256_kernel(const StftParam
 #pragma unroll
           for (int t = 0; t < 32; ++t) xs[t] = h32r_edge_sample(xc, P.n, p0 + 8 * t, P.left, P.padtype, P.x_origin);
         }
+        if (MODE == 1) {
+          float xb[32];
+          const int64_t p1 = p0 + 4 * (int64_t)P.hop;
+          if (fl + 4 >= nf) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = mul2<PK>(bc2(xs[t]), __ldg(P.wpair + c + 8 * t));
+            for (int t = 0; t < 32; ++t) xb[t] = 0.f;
+          } else if (p1 - c - P.left >= 0 && p1 - c + N - 1 - P.left < P.n) {
+            const float* xp = xc + (p1 - lo);
+#pragma unroll
+            for (int t = 0; t < 32; ++t) xb[t] = __ldg(xp + 8 * t);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) xb[t] = h32r_edge_sample(xc, P.n, p1 + 8 * t, P.left, P.padtype, P.x_origin);
+          }
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = mul2<PK>(make_float2(xs[t], xb[t]), bc2(__ldg(P.win + c + 8 * t)));
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = mul2<PK>(bc2(xs[t]), __ldg(P.wpair + c + 8 * t));
+        }
       }
       r1k_fft32<PK>(v);  // v[R1K_REG(kappa)] = Y_g[c][kappa]
 #pragma unroll
@@ -155,7 +177,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft256_kernel(const StftParam
           float2 B = make_float2(__shfl_sync(0xffffffffu, Bs.x, partner), __shfl_sync(0xffffffffu, Bs.y, partner));
           if (c0) B = j ? v[8 * (4 - j) + 7 - m] : v[(8 - m) & 7];  // c = 0 pairs with itself
           const int k = c + 8 * j + 32 * m;
-          const R1KItem it = r1k_item<MODE, SQZ, 128>(P, txs, col, nullptr, k, (float)k, A, B);
+          const R1KItem it = r1k_item<MODE, SQZ, 128>(P, txs, col, colB, k, (float)k, A, B);
           if (MODE == 0) {
             sval[k] = make_float2(it.vre, it.vim);
             skey[k] = it.kb;
@@ -163,7 +185,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft256_kernel(const StftParam
         }
       }
       if (c0) {
-        const R1KItem it = r1k_item<MODE, SQZ, 128>(P, txs, col, nullptr, 128, 128.f, v[4], v[4]);
+        const R1KItem it = r1k_item<MODE, SQZ, 128>(P, txs, col, colB, 128, 128.f, v[4], v[4]);
         if (MODE == 0) {
           sval[128] = make_float2(it.vre, it.vim);
           skey[128] = it.kb;
@@ -237,10 +259,8 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft256_kernel(const StftParam
   }
 }
 
-static ssq_status stft_r256_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
-  *done = false;
-  if (P.n_fft != 256 || getenv("SSQ_NO_R256")) return SSQ_OK;
-  constexpr int NW = 4, F = 16;
+template <int NW, int F>
+static ssq_status stft_r256_launch_f(ssq_ctx* ctx, StftParams& P, bool* done) {
   StftParams Q = P;
   Q.F = F;
   Q.acc_stride = R256_AS;
@@ -251,9 +271,9 @@ static ssq_status stft_r256_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   const size_t smem = ((size_t)F * R256_AS + (size_t)NW * 32 * R1K_XS) * sizeof(float2);
   const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx->num_sms * 3);
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
-  void (*k)(const StftParams) = P.mode == 1 ? ssq_stft256_kernel<1, 0, NW, F>
-                                : leb       ? ssq_stft256_kernel<0, 1, NW, F>
-                                            : ssq_stft256_kernel<0, 0, NW, F>;
+  void (*k)(const StftParams);
+  if constexpr (F == 32) k = ssq_stft256_kernel<1, 0, NW, F>;
+  else k = leb ? ssq_stft256_kernel<0, 1, NW, F> : ssq_stft256_kernel<0, 0, NW, F>;
   SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<grid, NW * 32, smem, ctx->stream>>>(Q);
   const char* name = P.mode == 1 ? "ssq_stft256_kernel<stft>" : "ssq_stft256_kernel<ssq>";
@@ -261,4 +281,11 @@ static ssq_status stft_r256_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   ctx->last_kernel = name;
   P.F = F;
   return SSQ_OK;
+}
+
+static ssq_status stft_r256_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
+  *done = false;
+  if (P.n_fft != 256 || getenv("SSQ_NO_R256")) return SSQ_OK;
+  // ssq: 16-frame tiles (one group of four frames per warp); stft: 32-frame tiles, two groups per FFT
+  return P.mode == 1 ? stft_r256_launch_f<4, 32>(ctx, P, done) : stft_r256_launch_f<4, 16>(ctx, P, done);
 }
