@@ -363,13 +363,20 @@ def run_other(args, rank, world, local_rank):
         abytes = ch * (4 * n + 8 * (N_FFT // 2 + 1) * nfr)
         desc = f"istft {ch}ch x {n} samples, n_fft=512 hop=32 (overlap-add + window norm + unpad)"
         step = lambda: eng.istft(Sx, win, N_FFT, HOP, N=n)
-    elif wl == "stft":
+    elif wl in ("stft", "ssq_stft"):
+        # the same 384 x 1.8 M recording at another geometry (--n-fft / --hop), e.g. the reference's
+        # multichannel script (n_fft 1024, hop 256) or its README (256 / 64)
         ch, n = args.channels, args.samples
+        nfft, hop = args.n_fft, args.hop
+        win = np.hanning(nfft)
         x = make_neural(torch, ch, n, FS, dev, 0x5351 + rank)
-        out = torch.empty((ch, N_FFT // 2 + 1, (n - 1) // HOP + 1), dtype=torch.complex64, device=dev)
-        abytes = algorithmic_bytes(ch, n)
-        desc = f"stft {ch}ch x {n} samples, n_fft=512 hop=32"
-        step = lambda: eng.stft(x, win, N_FFT, HOP, out=out)
+        out = torch.empty((ch, nfft // 2 + 1, (n - 1) // hop + 1), dtype=torch.complex64, device=dev)
+        abytes = algorithmic_bytes(ch, n, nfft, hop)
+        desc = f"{wl} {ch}ch x {n} samples, n_fft={nfft} hop={hop}"
+        if wl == "stft":
+            step = lambda: eng.stft(x, win, nfft, hop, out=out)
+        else:
+            step = lambda: eng.ssq_stft(x, win, nfft, hop, FS, out=out)
     else:
         ch, n = (8, 1 << 20) if args.channels == CHANNELS else (args.channels, args.samples)
         t = torch.arange(n, device=dev, dtype=torch.float64) / n
@@ -471,6 +478,8 @@ def main():
     ap.add_argument("--e2e-channels", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-samples", type=int, default=450_000, help="samples per step of the reference arm")
+    ap.add_argument("--n-fft", type=int, default=N_FFT, help="side workloads only: another STFT geometry")
+    ap.add_argument("--hop", type=int, default=HOP)
     ap.add_argument("--workload", default="ssq_stft", choices=["ssq_stft", "stft", "istft", "ssq_cwt"],
                     help="ssq_stft (default, BASELINE configs[1]) is the contract line; the others time the "
                          "remaining rows of SURVEY 8 (configs[3] istft 4096 ch x 300 k, configs[2] ssq_cwt on a "
@@ -482,7 +491,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
-    elif args.workload != "ssq_stft":
+    elif args.workload != "ssq_stft" or (args.n_fft, args.hop) != (N_FFT, HOP):
         run_other(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
