@@ -173,6 +173,43 @@ class Engine:
         return (out, sf) if return_freqs else out
 
 
+    def icwt(self, Wx, scales, wavelet="gmw", l1_norm=True, x_mean=0.0, exact_adm=False, x_len=None):
+        """Wx: complex64 CUDA [channels, ns, n_cols] -> x float32 [channels, x_len] (one-integral branch)."""
+        import torch
+        assert Wx.is_cuda and Wx.dtype == torch.complex64 and Wx.dim() == 3 and Wx.is_contiguous()
+        ch, ns, ncols = Wx.shape
+        sc = np.ascontiguousarray(scales, dtype=np.float64)
+        xl = ncols if x_len is None else int(x_len)
+        x = torch.empty((ch, xl), dtype=torch.float32, device=Wx.device)
+        flags = (0 if l1_norm else _lib.FLAG_L2_NORM) | (_lib.FLAG_ADM_EXACT if exact_adm else 0)
+        self._bind_stream()
+        st = load().ssq_icwt_batch_f32(self.ctx.handle, C.c_void_p(Wx.data_ptr()), ch, ns, ncols,
+                                       1 if wavelet == "morlet" else 0, C.c_void_p(sc.ctypes.data), 1, xl,
+                                       float(x_mean), flags, C.c_void_p(x.data_ptr()))
+        raise_status(st, self.ctx.handle)
+        return x
+
+    def issq_cwt(self, Tx, scales, wavelet="gmw"):
+        """Tx: complex64 CUDA [channels, ns, n] -> x float32 [channels, n] (full inversion)."""
+        import torch
+        assert Tx.is_cuda and Tx.dtype == torch.complex64 and Tx.dim() == 3 and Tx.is_contiguous()
+        ch, ns, n = Tx.shape
+        sc = np.ascontiguousarray(scales, dtype=np.float64)
+        x = torch.empty((ch, n), dtype=torch.float32, device=Tx.device)
+        self._bind_stream()
+        st = load().ssq_issq_cwt_batch_f32(self.ctx.handle, C.c_void_p(Tx.data_ptr()), ch, ns, n,
+                                           1 if wavelet == "morlet" else 0, C.c_void_p(sc.ctypes.data),
+                                           C.c_void_p(x.data_ptr()))
+        raise_status(st, self.ctx.handle)
+        return x
+
+    def default_scales(self, n, nv=32, simd=False):
+        ns = load().ssq_cwt_default_scales(int(n), int(nv), int(simd), C.c_void_p(0))
+        sc = np.empty(ns, dtype=np.float64)
+        load().ssq_cwt_default_scales(int(n), int(nv), int(simd), C.c_void_p(sc.ctypes.data))
+        return sc
+
+
 class SsqStftStream:
     """Streaming ssq_stft over chunks of an interleaved [samples, channels] recording (int16 or
     float32 CUDA tensors): the B200 replacement of the dask `map_overlap` caller

@@ -252,3 +252,33 @@ def test_cwt_against_upstream_golden():
         Wu, dWu = z[f"{wav}_Wx"], z[f"{wav}_dWx"]
         assert np.abs(r * Wx[rows] - Wu[rows]).max() < RTOL * np.abs(Wu).max(), wav
         assert np.abs(r * dWx[rows] - dWu[rows]).max() < RTOL * np.abs(dWu).max(), wav
+
+
+def test_full_size_round_trips_config3():
+    """BASELINE configs[2] size (2^20 samples, nv=32, 576 scales) on the device: cwt -> icwt and
+    ssq_cwt(maximal) -> issq_cwt give the chirp back (size-independent property; the oracle would need > 80 GB
+    in float64 at this size), and the squeezed transform keeps the column sums of Wx."""
+    import torch
+    from ssqueeze_rs_b200.batch import Engine
+    eng = Engine(0)
+    n = 1 << 20
+    t = torch.arange(n, device="cuda", dtype=torch.float64) / n
+    x = torch.sin(2 * np.pi * n * (0.002 * t + 0.5 * 0.2 * t * t)).to(torch.float32).view(1, -1).contiguous()
+    sc = eng.default_scales(n, 32)
+    assert len(sc) == 576
+    Wx = eng.cwt(x, "gmw", sc, fs=1.0)
+    xr = eng.icwt(Wx, sc, "gmw", exact_adm=True)
+    core = slice(n // 16, n - n // 16)
+    err = float((xr - x)[0, core].abs().mean())
+    assert err < 2e-2, err
+    colsum_W = Wx.sum(dim=1)
+    del Wx
+    torch.cuda.empty_cache()
+    Tx = eng.ssq_cwt(x, "gmw", sc, fs=1.0, maprange="maximal")
+    xs = eng.issq_cwt(Tx, sc, "gmw")
+    err2 = float((xs - x)[0, core].abs().mean())
+    assert err2 < 2e-2, err2
+    # ssqueezing only moves coefficients along the scale axis (those whose bin falls outside the grid are dropped)
+    colsum_T = Tx.sum(dim=1)
+    rel_cs = float((colsum_T - colsum_W)[0, core].abs().mean() / colsum_W[0, core].abs().mean())
+    assert rel_cs < 5e-2, rel_cs
