@@ -377,6 +377,30 @@ def run_other(args, rank, world, local_rank):
             step = lambda: eng.stft(x, win, nfft, hop, out=out)
         else:
             step = lambda: eng.ssq_stft(x, win, nfft, hop, FS, out=out)
+    elif wl == "c5":
+        # BASELINE configs[4]: 1024 channels x 10 min @ 30 kHz (18 M samples), strong scaling: 1024 / world channels
+        # per GPU, resident input (73.7 GB at world 1), Tx written through a ring of two 16-channel buffers
+        # (18.5 GB each) as the host gather would drain them.  Input: white noise + two tones (the neural recipe
+        # needs an 18 M-point FFT per channel block to generate).
+        ch_total, n = (1024, 18_000_000) if args.channels == CHANNELS else (args.channels, args.samples)
+        ch = ch_total // world
+        blk = 16
+        x = torch.empty((ch, n), dtype=torch.float32, device=dev)
+        tt = torch.arange(n, device=dev, dtype=torch.float32) / FS
+        tone = 20.0 * torch.sin(2 * np.pi * 8.0 * tt) + 5.0 * torch.sin(2 * np.pi * 60.0 * tt)
+        for c0 in range(0, ch, blk):
+            x[c0:c0 + blk] = torch.randn((min(blk, ch - c0), n), generator=g, device=dev) * 10 + tone
+        del tt, tone
+        nfr = (n - 1) // HOP + 1
+        ring = [torch.empty((blk, N_FFT // 2 + 1, nfr), dtype=torch.complex64, device=dev) for _ in range(2)]
+        abytes = algorithmic_bytes(ch, n)
+        desc = (f"ssq_stft configs[4]: {ch_total}ch x {n} samples over {world} GPU(s), {ch} ch per GPU in blocks of "
+                f"{blk} through a ring of 2 output buffers, n_fft=512 hop=32; white noise + tones")
+
+        def step():
+            for i, c0 in enumerate(range(0, ch, blk)):
+                m = min(blk, ch - c0)
+                eng.ssq_stft(x[c0:c0 + m], win, N_FFT, HOP, FS, out=ring[i & 1][:m])
     else:
         ch, n = (8, 1 << 20) if args.channels == CHANNELS else (args.channels, args.samples)
         t = torch.arange(n, device=dev, dtype=torch.float64) / n
@@ -408,7 +432,7 @@ def run_other(args, rank, world, local_rank):
     if rank == 0:
         print(json.dumps({
             "metric": f"{wl} input Msamples/s", "value": per_s / 1e6, "unit": "Msamples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if wl == "c5" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": desc},
             "roofline": {"bound": "hbm", "achieved": abytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": abytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
@@ -480,7 +504,7 @@ def main():
     ap.add_argument("--ref-samples", type=int, default=450_000, help="samples per step of the reference arm")
     ap.add_argument("--n-fft", type=int, default=N_FFT, help="side workloads only: another STFT geometry")
     ap.add_argument("--hop", type=int, default=HOP)
-    ap.add_argument("--workload", default="ssq_stft", choices=["ssq_stft", "stft", "istft", "ssq_cwt"],
+    ap.add_argument("--workload", default="ssq_stft", choices=["ssq_stft", "stft", "istft", "ssq_cwt", "c5"],
                     help="ssq_stft (default, BASELINE configs[1]) is the contract line; the others time the "
                          "remaining rows of SURVEY 8 (configs[3] istft 4096 ch x 300 k, configs[2] ssq_cwt on a "
                          "channel cut of 2^20 samples, stft on configs[1]) with the same JSON layout")
