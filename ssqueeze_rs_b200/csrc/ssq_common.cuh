@@ -42,6 +42,9 @@ struct ssq_ctx {
   DevBuf cwt_tw;
   int64_t cwt_tw_n = -1;
   DevBuf cwt_scales;
+  // pinned staging of the float64 entry points (two chunks: copy of chunk i+1 overlaps the conversion of chunk i)
+  void* pin[2] = {nullptr, nullptr};
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
 };
 
 static thread_local std::string g_tls_err;
