@@ -38,9 +38,10 @@ CHANNELS = 384
 SAMPLES = 1_800_000
 WORKLOAD = "ssq_stft 384ch x 1.8M samples (60 s @ 30 kHz) synthetic neural, n_fft=512 hop=32 hann reflect"
 # dram__bytes_read.sum + dram__bytes_write.sum of one 384-channel launch of the dominant kernel, from the ncu
-# pass over this same command (profiles/r1k_bench_launches.csv: 3.79 GB read + 45.37 GB written; the
-# algorithmic figure is 2.76 + 44.41 GB).  Only valid for the default workload; null otherwise.
-NCU_DRAM_BYTES_PER_LAUNCH = 49.16e9
+# pass over this same command (profiles/r1q_bench_launches.csv: 5.9 GB read + 47.2 GB written; the
+# algorithmic figure is 2.76 + 44.41 GB; the r1k capture earlier in the round read 3.79 + 45.37 GB).
+# Only valid for the default workload; null otherwise.
+NCU_DRAM_BYTES_PER_LAUNCH = 53.1e9
 
 
 def algorithmic_bytes(channels, n, n_fft=N_FFT, hop=HOP):
