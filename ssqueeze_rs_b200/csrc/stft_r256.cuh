@@ -52,7 +52,7 @@ __device__ __noinline__ void r256_collision(float2* col, unsigned char* T, int k
 
 // NW warps per CTA, F frames per tile (groups of four per warp).
 template <int MODE, int SQZ, int NW, int F>
-__global__ void __launch_bounds__(NW * 32, 3) ssq_stft256_kernel(const StftParams P) {
+__global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel(const StftParams P) {
   constexpr int N = 256, AS = R256_AS, XS = R1K_XS, SS = R256_SS, GPW = F / (4 * NW);
   constexpr bool PK = SSQ_PK_DEFAULT;
   static_assert(F % (4 * NW) == 0, "a warp takes its frames four at a time");
@@ -269,7 +269,7 @@ static ssq_status stft_r256_launch_f(ssq_ctx* ctx, StftParams& P, bool* done) {
   if (Q.total_tiles > (int64_t)0x7ff00000) return SSQ_OK;
   *done = true;
   const size_t smem = ((size_t)F * R256_AS + (size_t)NW * 32 * R1K_XS) * sizeof(float2);
-  const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx->num_sms * 3);
+  const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx->num_sms * (F == 32 ? 3 : 4));
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
   void (*k)(const StftParams);
   if constexpr (F == 32) k = ssq_stft256_kernel<1, 0, NW, F>;
