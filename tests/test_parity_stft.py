@@ -609,3 +609,43 @@ def test_modulated_fast_path_and_issq_roundtrip_512():
     y = rs.issq_stft(Tx, win, n_fft=512, hop_len=1, fs=250.0)
     sh = 512 // 2 - (512 - 1) // 2
     assert np.abs(y[:len(x) - sh] - x[sh:]).mean() < 0.1
+
+
+def test_fast_kernels_randomised_sweep():
+    """Seeded sweep over the three register-FFT kernels (n_fft 256 / 512 / 1024): random lengths (including shorter
+    than n_fft and lengths that leave ragged tiles), hops, window families and lengths (win_len < n_fft is centre
+    padded, ssq_stft.rs:104-119), padding, squeezing, gamma, modulation -- each against the float64 oracle."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    rng = np.random.default_rng(20261018)
+    wins = {"hann": np.hanning, "hamming": np.hamming, "blackman": np.blackman,
+            "rand": lambda m: 0.2 + rng.random(m)}
+    for case in range(36):
+        n_fft = (256, 512, 1024)[case % 3]
+        N = int(rng.choice([rng.integers(1, n_fft), rng.integers(n_fft, 6 * n_fft), rng.integers(6 * n_fft, 40 * n_fft)]))
+        hop = int(rng.choice([1, 2, 31, 32, 33, 64, 100, 256, n_fft, n_fft + 17])) if N > 2000 else int(rng.integers(1, 70))
+        if N // hop > 6000:
+            hop = max(hop, N // 6000)
+        wname = list(wins)[case % 4]
+        win_len = n_fft if case % 5 else int(rng.integers(n_fft // 4, n_fft))
+        win = np.asarray(wins[wname](win_len), dtype=np.float64)
+        kw = dict(padtype=("reflect", "zero")[case % 2], squeezing=("sum", "lebesgue")[(case // 2) % 2 if case % 7 == 0 else 0],
+                  gamma=(None, 1e-3, 5.0)[case % 3 if case % 4 == 0 else 0], modulated=bool(case % 6 == 5))
+        fs = float(rng.choice([1.0, 1000.0, 30000.0]))
+        x = rng.standard_normal(N) * rng.choice([1e-3, 1.0, 300.0])
+        if case % 9 == 4:
+            x += 5.0 * np.abs(x).max() * np.sin(2 * np.pi * 0.123 * np.arange(N))
+        Tx, sf = rs.ssq_stft(x, win, n_fft=n_fft, hop_len=hop, fs=fs, **kw)
+        name = _lib.default_context().last_kernel_name()
+        assert str(n_fft) in name and "generic" not in name, (case, name)
+        To, sfo = O.ssq_stft(x, win, n_fft=n_fft, hop_len=hop, fs=fs, **kw)
+        assert Tx.shape == To.shape, (case, Tx.shape, To.shape)
+        assert np.allclose(sf, sfo, rtol=1e-15, atol=0)
+        sc = max(np.abs(To).max(), 1e-300)
+        assert np.abs(Tx.sum(0) - To.sum(0)).max() < 40 * RTOL * sc, (case, n_fft, N, hop, wname, kw)
+        bad = np.abs(Tx - To) > RTOL * sc
+        assert bad.mean() < 1e-2, (case, n_fft, N, hop, wname, kw, float(bad.mean()))
+        if win_len == n_fft:
+            Sx, _ = rs.stft(x, n_fft, hop, win, kw["padtype"])
+            So, _ = O.stft(x, n_fft, hop, win, kw["padtype"])
+            assert rel(Sx, So) < RTOL, (case, n_fft, N, hop, wname)
