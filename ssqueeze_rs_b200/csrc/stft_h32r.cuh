@@ -149,9 +149,17 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
       unsigned char* T = (r & 1) ? tagB : tagA;
       unsigned char* Tn = (r & 1) ? tagA : tagB;
       const bool on = cur.kb >= 0;
+      // the accumulator is read together with the tag (speculatively: it is only used when no other lane aims at
+      // the same bin in this step, and then nobody else writes it), so the two shared-memory latencies overlap
+      float2* slot = col + h32r_phys(on ? cur.kb : 0);
+      float2 t = *slot;
       const bool mine = !on || T[cur.kb] == (unsigned char)lane;
       if (__all_sync(0xffffffffu, mine)) {
-        if (on) smem_rmw_add(col + h32r_phys(cur.kb), cur.vre, cur.vim);
+        if (on) {
+          t.x += cur.vre;
+          t.y += cur.vim;
+          *slot = t;
+        }
       } else {
         h32r_collision(col, T, cur.kb, cur.vre, cur.vim, mine, lane);
       }

@@ -220,9 +220,15 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
           unsigned char* T = (i & 1) ? tagB : tagA;
           unsigned char* Tn = (i & 1) ? tagA : tagB;
           const bool on = cur.kb >= 0;
+          float2* slot = col + (on ? cur.kb : 0);  // read with the tag: the two shared-memory latencies overlap
+          float2 t = *slot;
           const bool mine = !on || T[cur.kb] == (unsigned char)lane;
           if (__all_sync(0xffffffffu, mine)) {
-            if (on) smem_rmw_add(col + cur.kb, cur.vre, cur.vim);
+            if (on) {
+              t.x += cur.vre;
+              t.y += cur.vim;
+              *slot = t;
+            }
           } else {
             r256_collision(col, T, cur.kb, cur.vre, cur.vim, mine, lane);
           }
