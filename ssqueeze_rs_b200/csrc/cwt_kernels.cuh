@@ -303,6 +303,16 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
       if (inv) x.y = -x.y;
       v[u] = x;
     }
+  } else if (P.load_mode == 0) {
+    // plain row of a previous pass: one base pointer, 32-bit in-row offsets (the generic functor spent 18
+    // instructions per load on 64-bit index arithmetic and mode checks: 29 % of the pass, ncu r1s)
+    const float2* inrow = P.in + (size_t)row * L + (j + g * Q);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = inrow[(unsigned)(8 * u) * (unsigned)Q];
+    if (inv) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u].y = -v[u].y;
+    }
   } else {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
@@ -384,6 +394,14 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
     for (int i = 0; i < 16; ++i) {
       const int e = threadIdx.x + 8 * TC * i;
       store((j0 << 7) + e, buf[(e >> 7) * 129 + (e & 127)]);
+    }
+  } else if (P.store_mode == 0) {
+    // intermediate pass: whole rows, no window, no scaling
+    float2* orow = P.out + (size_t)row * L + (((j - kk) << 7) + kk + g * Ns);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      orow[(unsigned)(16 * k2) * (unsigned)Ns] = a[k2];
+      orow[(unsigned)(16 * k2 + 8) * (unsigned)Ns] = b[k2];
     }
   } else {
     const int base = ((j - kk) << 7) + kk;
