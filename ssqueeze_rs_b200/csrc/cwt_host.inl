@@ -196,6 +196,7 @@ static ssq_status cwt_inverse_rows(ssq_ctx* ctx, const CwtCall& c, int log2L, co
   B.n1 = n1;
   B.out_scale = out_scale;
   B.l2_norm = (c.flags & SSQ_FLAG_L2_NORM) ? 1 : 0;
+  if (g1 > (int64_t)0x7fffffff) return ssq_fail(ctx, SSQ_EUNSUPPORTED, "cwt: more than 2^31 rows in one call");
   // rows are ordered (channel, scale, which): cut the range into runs of equal skip level
   int64_t r0 = g0;
   while (r0 < g1) {

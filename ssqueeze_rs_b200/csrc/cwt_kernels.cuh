@@ -276,12 +276,16 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   if (P.load_mode == 2) {
     // x-hat * psi-hat generated on the fly: the row's constants once per thread, and an exact integer
     // early-out -- psihat() returns 0 beyond its cut-off, i.e. for spectrum indices >= blim
-    const int64_t gr = P.row0 + row;
-    const int which = (int)(gr % P.nd);
-    const int64_t cs = gr / P.nd;
-    const float scale = __ldg(P.scales + (int)(cs % P.ns));
-    const float2* xh = P.xhat + (size_t)(cs / P.ns) * L;
+    // 32-bit row arithmetic (the host refuses more than 2^31 rows): three 64-bit divisions per thread were
+    // 7.6 % of a generation pass
+    const unsigned gr = (unsigned)P.row0 + (unsigned)row;
+    const unsigned cs = gr / (unsigned)P.nd;
+    const int which = (int)(gr - cs * (unsigned)P.nd);
+    const unsigned chn = cs / (unsigned)P.ns;
+    const float scale = __ldg(P.scales + (int)(cs - chn * (unsigned)P.ns));
+    const float2* xh = P.xhat + (size_t)chn * L;
     const float cut = P.wavelet == SSQ_WAVELET_MORLET ? 14.5f : 4.5f;
+    const float inv_L = 1.f / (float)L;
     int blim = (L >> 1) + 1;  // negative frequencies: psi-hat = 0 (cwt.rs:496-541)
     if (scale > 0.f) blim = (int)fminf((float)blim, cut * (float)L / (6.283185307179586f * scale) * 1.0001f + 2.f);
 #pragma unroll
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
       const int idx = (j + (g + 8 * u) * Q) >> P.up_shift;
       float2 x = make_float2(0.f, 0.f);
       if (idx < blim) {
-        const float xi = 6.283185307179586f * (float)idx / (float)L;  // wavelets/base.rs:18-33, idx <= L/2
+        const float xi = (6.283185307179586f * (float)idx) * inv_L;  // wavelets/base.rs:18-33, idx <= L/2 (L = 2^k: exact)
         const float ps = psihat(P.wavelet, scale * xi);
         if (ps != 0.f) {
           const float2 h = __ldg(xh + idx);
@@ -369,11 +373,11 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   float sscale = 1.f;
   int soff = 0, scols = L;
   if (P.store_mode == 1) {
-    const int64_t gr = P.row0 + row;
-    const int64_t cs = gr / P.nd;  // channel * ns + scale
-    sdst = ((gr % P.nd) ? P.outD : P.outW) + (size_t)cs * P.out_cols;
+    const unsigned gr = (unsigned)P.row0 + (unsigned)row;
+    const unsigned cs = gr / (unsigned)P.nd;  // channel * ns + scale
+    sdst = ((gr - cs * (unsigned)P.nd) ? P.outD : P.outW) + (size_t)cs * P.out_cols;
     sscale = P.out_scale;
-    if (P.l2_norm) sscale *= sqrtf(__ldg(P.scales + (int)(cs % P.ns)));  // cwt.rs:253
+    if (P.l2_norm) sscale *= sqrtf(__ldg(P.scales + (int)(cs % (unsigned)P.ns)));  // cwt.rs:253
     soff = (int)P.n1;
     scols = (int)P.out_cols;
   }
@@ -390,10 +394,19 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
       buf[c * 129 + g + 8 + 16 * k2] = b[k2];
     }
     __syncthreads();
+    if (P.store_mode == 0) {
+      float2* orow = P.out + (size_t)row * L + (j0 << 7) + threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int e = threadIdx.x + 8 * TC * i;
-      store((j0 << 7) + e, buf[(e >> 7) * 129 + (e & 127)]);
+      for (int i = 0; i < 16; ++i) {
+        const int e = threadIdx.x + 8 * TC * i;
+        orow[8 * TC * i] = buf[(e >> 7) * 129 + (e & 127)];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int e = threadIdx.x + 8 * TC * i;
+        store((j0 << 7) + e, buf[(e >> 7) * 129 + (e & 127)]);
+      }
     }
   } else if (P.store_mode == 0) {
     // intermediate pass: whole rows, no window, no scaling
