@@ -60,9 +60,9 @@ __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, fl
   const float num0 = fmaf(b0, c, -a * d0);
   const float q0 = num0 * rcp_approx(den);
   const float binf = fabsf(fmaf(-q0, P.cphase, skf));
-  const float r = ceilf(binf - 0.5f);
-  it.kb = (int)fminf(fmaxf(r, 0.f), 256.f);  // fmaxf(NaN, 0) = 0 -> bin 0 like the reference
-  if (den < P.gate2) it.kb = -1;              // |Sx| < gamma (ssq_stft.rs:23): dropped
+  // nearest grid point, ties to the lower index, clamped; NaN converts to 0 -> bin 0 like the reference
+  it.kb = min(max(__float2int_ru(binf - 0.5f), 0), 256);
+  if (den < P.gate2) it.kb = -1;  // |Sx| < gamma (ssq_stft.rs:23): dropped
   if (SQZ == SSQ_SQUEEZE_LEBESGUE) {
     it.vre = P.leb_val;
     it.vim = 0.f;
