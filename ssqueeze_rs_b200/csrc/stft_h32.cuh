@@ -182,9 +182,19 @@ __device__ __forceinline__ void h32_fft512(const H32Lane& L, float2* xch, float2
     // (W^{t (512 - e_a)}), except for lane 0 whose partner is j = 32: W^{480 t} = conj(W_16^t)
     const float C1 = 0.92387953251128673848f, S1 = 0.38268343236508978178f, H = 0.70710678118654752440f;
     const float2 w16[7] = {{C1, -S1}, {H, -H}, {S1, -C1}, {0.f, -1.f}, {-S1, -C1}, {-H, -H}, {-C1, -S1}};
+    // stage-3 twiddles W^{t e_a} as powers of the first (at most 3 products deep): 12 registers of table
+    // traded for 6 complex multiplications -- the kernel is bound by latency, not by issue slots
+    float2 w3[7];
+    w3[0] = L.tw3a[0];
+    w3[1] = cmulf<PK>(w3[0], w3[0]);
+    w3[2] = cmulf<PK>(w3[1], w3[0]);
+    w3[3] = cmulf<PK>(w3[1], w3[1]);
+    w3[4] = cmulf<PK>(w3[3], w3[0]);
+    w3[5] = cmulf<PK>(w3[3], w3[1]);
+    w3[6] = cmulf<PK>(w3[3], w3[2]);
 #pragma unroll
     for (int t = 1; t < 8; ++t) {
-      const float2 wa = L.tw3a[t - 1];
+      const float2 wa = w3[t - 1];
       va[t] = cmulf<PK>(va[t], wa);
       const float2 wb = L.l0 ? w16[t - 1] : wa;
       vb[t] = cmulcf<PK>(vb[t], wb);  // vb * conj(wb)
