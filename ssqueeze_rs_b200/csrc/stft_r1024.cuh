@@ -15,7 +15,9 @@
 #pragma once
 #include "stft_h32r.cuh"
 
-#define R1K_AS 515  // column stride of the Tx tile (float2): odd, >= 513
+#define R1K_AS 514  // column stride of the Tx tile (float2), >= 513.  The read-out's half-warp covers 8 frames x 2 row
+                    // groups: banks (2 AS fr + 2 v) mod 32 must be distinct -> 2 AS = 4 mod 32 (515 gave 2-way conflicts:
+                    // 128 instead of 64 wavefronts per frame, ncu r1t)
 #define R1K_XS 33   // exchange row stride (float2)
 
 __host__ __device__ constexpr float r1k_q(int j) {  // cos(pi j / 16), j = 0..8
