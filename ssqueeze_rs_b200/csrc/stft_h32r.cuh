@@ -73,7 +73,7 @@ __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, fl
   return it;
 }
 
-__device__ __noinline__ void h32r_collision(float2* col, unsigned char* T, int kb, float vre, float vim, bool mine,
+__device__ __noinline__ void h32r_collision(float2* col, unsigned* T, int kb, float vre, float vim, bool mine,
                                             int lane) {
   const bool on = kb >= 0;
   {  // tonal frames: every active lane aims at the same bin -> one shuffle reduction, one add
@@ -112,8 +112,11 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
                                            float2* xch, float2* col, float2* colB, float2 (&va)[8], float2 (&vb)[8]) {
   const int lane = L.lane;
   const bool l0 = L.l0;
-  unsigned char* tagA = reinterpret_cast<unsigned char*>(xch);  // tags alias the exchange buffer
-  unsigned char* tagB = tagA + 264;
+  // tags alias the exchange buffer; one 32-bit word per destination bin: with byte tags four bins share a bank
+  // word and the lanes of a step, whose bins differ by multiples of 64, collided two ways (ncu r1r: 30
+  // wavefronts per frame for an ideal 15)
+  unsigned* tagA = reinterpret_cast<unsigned*>(xch);
+  unsigned* tagB = tagA + 264;
   h32_fft512<true, true, MODE == 0>(L, xch, va, vb);
   __syncwarp();  // stage-3 reads done before the tags overwrite the buffer
 
@@ -132,7 +135,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
     cur = h32r_item<MODE, SQZ>(P, txs, col, colB, skf, A, B);
   }
   if (MODE == 0) {
-    if (cur.kb >= 0) tagA[cur.kb] = (unsigned char)lane;
+    if (cur.kb >= 0) tagA[cur.kb] = (unsigned)lane;
     __syncwarp();
   }
 #pragma unroll
@@ -146,14 +149,14 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
       nxt = h32r_item<MODE, SQZ>(P, txs, col, colB, skf, A, B);
     }
     if (MODE == 0) {
-      unsigned char* T = (r & 1) ? tagB : tagA;
-      unsigned char* Tn = (r & 1) ? tagA : tagB;
+      unsigned* T = (r & 1) ? tagB : tagA;
+      unsigned* Tn = (r & 1) ? tagA : tagB;
       const bool on = cur.kb >= 0;
       // the accumulator is read together with the tag (speculatively: it is only used when no other lane aims at
       // the same bin in this step, and then nobody else writes it), so the two shared-memory latencies overlap
       float2* slot = col + h32r_phys(on ? cur.kb : 0);
       float2 t = *slot;
-      const bool mine = !on || T[cur.kb] == (unsigned char)lane;
+      const bool mine = !on || T[cur.kb] == (unsigned)lane;
       if (__all_sync(0xffffffffu, mine)) {
         if (on) {
           t.x += cur.vre;
@@ -163,7 +166,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
       } else {
         h32r_collision(col, T, cur.kb, cur.vre, cur.vim, mine, lane);
       }
-      if (r < 7 && nxt.kb >= 0) Tn[nxt.kb] = (unsigned char)lane;
+      if (r < 7 && nxt.kb >= 0) Tn[nxt.kb] = (unsigned)lane;
       __syncwarp();
     }
     cur = nxt;
