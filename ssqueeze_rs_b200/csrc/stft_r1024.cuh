@@ -19,6 +19,7 @@
                     // groups: banks (2 AS fr + 2 v) mod 32 must be distinct -> 2 AS = 4 mod 32 (515 gave 2-way conflicts:
                     // 128 instead of 64 wavefronts per frame, ncu r1t)
 #define R1K_XS 33   // exchange row stride (float2)
+#define R1K_WS 1300 // per-warp scratch (float2): max(32 * 33 exchange, 520 item values + 260 (520 keys) + 520 (2 x 520 tag words))
 
 __host__ __device__ constexpr float r1k_q(int j) {  // cos(pi j / 16), j = 0..8
   constexpr float q[9] = {1.f,
@@ -115,7 +116,7 @@ __device__ __forceinline__ R1KItem r1k_item(const StftParams& P, float txs, floa
 }
 
 // Rare path of a reassignment step (two lanes aim at one bin): see h32r_collision.
-__device__ __noinline__ void r1k_collision(float2* col, unsigned char* T, int kb, float vre, float vim, bool mine,
+__device__ __noinline__ void r1k_collision(float2* col, unsigned* T, int kb, float vre, float vim, bool mine,
                                            int lane) {
   const bool on = kb >= 0;
   {
@@ -156,12 +157,12 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
   extern __shared__ float2 smem[];
   float2* acc = smem;  // [F][AS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float2* xch = acc + F * AS + warp * (32 * XS);
+  float2* xch = acc + F * AS + warp * R1K_WS;
   // after the second DFT the exchange buffer holds the parked items and the tags
-  float2* sval = xch;                                          // [513] (520)
-  int* skey = reinterpret_cast<int*>(xch + 520);               // [513] (520 ints = 260 float2)
-  unsigned char* tagA = reinterpret_cast<unsigned char*>(xch + 780);  // [513] (520)
-  unsigned char* tagB = tagA + 520;
+  float2* sval = xch;                                            // [513] (520)
+  int* skey = reinterpret_cast<int*>(xch + 520);                 // [513] (520 ints = 260 float2)
+  unsigned* tagA = reinterpret_cast<unsigned*>(xch + 780);       // [513] (520 words = 260 float2): one word per
+  unsigned* tagB = tagA + 520;                                   // bin, so that no two bins share a bank word
 
   for (int i = threadIdx.x; i < F * AS; i += blockDim.x) acc[i] = make_float2(0.f, 0.f);
   const bool l0 = lane == 0;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
           cur.vre = sv.x;
           cur.vim = sv.y;
         }
-        if (cur.kb >= 0) tagA[cur.kb] = (unsigned char)lane;
+        if (cur.kb >= 0) tagA[cur.kb] = (unsigned)lane;
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 17; ++i) {
@@ -289,12 +290,12 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
             nxt.vre = sv.x;
             nxt.vim = sv.y;
           }
-          unsigned char* T = (i & 1) ? tagB : tagA;
-          unsigned char* Tn = (i & 1) ? tagA : tagB;
+          unsigned* T = (i & 1) ? tagB : tagA;
+          unsigned* Tn = (i & 1) ? tagA : tagB;
           const bool on = cur.kb >= 0;
           float2* slot = col + (on ? cur.kb : 0);  // read with the tag: the two shared-memory latencies overlap
           float2 t = *slot;
-          const bool mine = !on || T[cur.kb] == (unsigned char)lane;
+          const bool mine = !on || T[cur.kb] == (unsigned)lane;
           if (__all_sync(0xffffffffu, mine)) {
             if (on) {
               t.x += cur.vre;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
           } else {
             r1k_collision(col, T, cur.kb, cur.vre, cur.vim, mine, lane);
           }
-          if (i < 16 && nxt.kb >= 0) Tn[nxt.kb] = (unsigned char)lane;
+          if (i < 16 && nxt.kb >= 0) Tn[nxt.kb] = (unsigned)lane;
           __syncwarp();
           cur = nxt;
         }
@@ -348,7 +349,7 @@ static ssq_status stft_r1024_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   Q.total_tiles = Q.tiles_per_channel * P.channels;
   if (Q.total_tiles > (int64_t)0x7ff00000) return SSQ_OK;
   *done = true;
-  const size_t smem = ((size_t)F * R1K_AS + (size_t)NW * 32 * R1K_XS) * sizeof(float2);
+  const size_t smem = ((size_t)F * R1K_AS + (size_t)NW * R1K_WS) * sizeof(float2);
   const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx->num_sms * 3);
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
   void (*k)(const StftParams) = P.mode == 1 ? ssq_stft1024_kernel<1, 0, NW, F>
