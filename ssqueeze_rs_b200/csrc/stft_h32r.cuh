@@ -23,6 +23,11 @@
 #pragma once
 #include "stft_h32.cuh"
 
+#ifndef H32R_PK
+#define H32R_PK(MODE) true  // packed fp32x2 arithmetic in the FFT, both modes (the stft mode spilled with it until the
+                            // stage-3 twiddle table left the registers: 15.8 ms packed vs 16.6 ms scalar on 384 channels;
+                            // packing its window multiply and split as well spills again: 16.9 ms)
+#endif
 #define H32R_AS 261  // column stride (float2): bin k at k + (k >> 6) (max 260); odd
 
 __device__ __forceinline__ int h32r_phys(int k) { return k + (k >> 6); }
@@ -117,7 +122,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
   // wavefronts per frame for an ideal 15)
   unsigned* tagA = reinterpret_cast<unsigned*>(xch);
   unsigned* tagB = tagA + 264;
-  h32_fft512<true, true, MODE == 0>(L, xch, va, vb);
+  h32_fft512<true, true, H32R_PK(MODE)>(L, xch, va, vb);
   __syncwarp();  // stage-3 reads done before the tags overwrite the buffer
 
   // pair of step r: lanes >= 1 (va[r], vb[r]); lane 0: r < 4: (va[r], va[(8-r)&7]), r >= 4: (vb[11-r], vb[r-4])
