@@ -448,31 +448,47 @@ struct SsqCwtParams {
 __global__ void ssq_cwt_reassign_kernel(const SsqCwtParams P) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.n) return;
-  for (int i = 0; i < P.ns; ++i) {
-    float2 Wv = P.W[(size_t)i * P.n + b];
-    float2 Dv = P.D[(size_t)i * P.n + b];
-    const float mag = hypotf(Wv.x, Wv.y);
-    if (mag < P.gate) continue;  // ssq_cwt.rs:29-30
-    float c = Wv.x, d = Wv.y, a = Dv.x, bb = Dv.y;
-    if (mag < 1e-15f) {  // keep c*c+d*d away from fp32 underflow; the ratio is scale-free
-      const float up = 1.8446744e19f;  // 2^64
-      c *= up; d *= up; a *= up; bb *= up;
-    } else if (mag > 1e15f) {
-      const float dn = 5.4210109e-20f;  // 2^-64
-      c *= dn; d *= dn; a *= dn; bb *= dn;
+  const float2* __restrict__ Wc = P.W + b;
+  const float2* __restrict__ Dc = P.D + b;
+  float2* Tc = P.Tx + b;
+  // The loop used to be one latency chain per scale (load W, D -> bin -> load Tx -> store Tx, in program order
+  // because Tx may alias W / D for the compiler): 2.9 ms per channel for 11.9 GB.  Now the W, D values of eight
+  // scales are in flight at once, and the thread -- the only writer of its column -- adds to Tx with a reduction
+  // (no value returned: nothing to wait for; same-thread reductions to one address stay in program order).
+  constexpr int U = 8;
+  for (int i0 = 0; i0 < P.ns; i0 += U) {
+    float2 Wb[U], Db[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(i0 + u, P.ns - 1);
+      Wb[u] = __ldcs(Wc + (size_t)i * P.n);
+      Db[u] = __ldcs(Dc + (size_t)i * P.n);
     }
-    const float w = fabsf((bb * c - a * d) / ((c * c + d * d) * 6.283185307179586f));
-    if (!(w <= 3.4028235e38f)) continue;  // inf / NaN skipped (:167-169)
-    const float v = P.is_log ? (log2f(w) - P.f0) * P.inv_step : (w - P.f0) * P.inv_step;
-    const float r = roundf(v);  // f64::round: half away from zero (:176, :187)
-    if (!(r >= 0.f && r < (float)P.ns)) continue;  // out of range dropped (:177-179)
-    const int bin = (int)r;
-    const int k = P.flipud ? P.ns - 1 - bin : bin;
-    float2* t = P.Tx + (size_t)k * P.n + b;
-    float2 cur = *t;
-    if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) cur.x += P.leb_val;
-    else { cur.x += Wv.x * P.K; cur.y += Wv.y * P.K; }
-    *t = cur;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u >= P.ns) break;
+      const float2 Wv = Wb[u], Dv = Db[u];
+      const float mag = hypotf(Wv.x, Wv.y);
+      if (mag < P.gate) continue;  // ssq_cwt.rs:29-30
+      float c = Wv.x, d = Wv.y, a = Dv.x, bb = Dv.y;
+      if (mag < 1e-15f) {  // keep c*c+d*d away from fp32 underflow; the ratio is scale-free
+        const float up = 1.8446744e19f;  // 2^64
+        c *= up; d *= up; a *= up; bb *= up;
+      } else if (mag > 1e15f) {
+        const float dn = 5.4210109e-20f;  // 2^-64
+        c *= dn; d *= dn; a *= dn; bb *= dn;
+      }
+      const float w = fabsf((bb * c - a * d) / ((c * c + d * d) * 6.283185307179586f));
+      if (!(w <= 3.4028235e38f)) continue;  // inf / NaN skipped (:167-169)
+      const float v = P.is_log ? (log2f(w) - P.f0) * P.inv_step : (w - P.f0) * P.inv_step;
+      const float r = roundf(v);  // f64::round: half away from zero (:176, :187)
+      if (!(r >= 0.f && r < (float)P.ns)) continue;  // out of range dropped (:177-179)
+      const int bin = (int)r;
+      const int k = P.flipud ? P.ns - 1 - bin : bin;
+      float2* t = Tc + (size_t)k * P.n;
+      if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) atomicAdd(&t->x, P.leb_val);
+      else atomicAdd(t, make_float2(Wv.x * P.K, Wv.y * P.K));
+    }
   }
 }
 
