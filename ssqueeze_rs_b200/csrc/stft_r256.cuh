@@ -13,11 +13,15 @@
 #pragma once
 #include "stft_r1024.cuh"
 
-#define R256_AS 131  // column stride of the Tx tile (float2): odd, >= 129
+#define R256_AS 145  // column stride of the Tx tile (float2); frame f's column starts at f * 145 + 8 (f & 1).
+                     // 145 = 1 mod 16 and the 8-slot stagger of odd frames put the two frames of a half-warp
+                     // (bins 17 c + i each) on disjoint banks in the reassignment step (stride 131: 55 wavefronts
+                     // per frame for an ideal 17, ncu r1v) and keep the read-out (16 frames x one row) conflict-free
+#define R256_WS 1088 // per-warp scratch (float2): max(32 * 33 exchange, 544 item values + 272 keys + 272 (16-bit tags))
 #define R256_SS 136  // per-frame stride of the parked items / tags (>= 8 * 17)
 
 // Rare path of a reassignment step; the four groups of a warp work on different columns.
-__device__ __noinline__ void r256_collision(float2* col, unsigned char* T, int kb, float vre, float vim, bool mine,
+__device__ __noinline__ void r256_collision(float2* col, unsigned short* T, int kb, float vre, float vim, bool mine,
                                             int lane) {
   const bool on = kb >= 0;
   {
@@ -37,9 +41,9 @@ __device__ __noinline__ void r256_collision(float2* col, unsigned char* T, int k
       return;
     }
   }
-  if (on && !mine) T[kb] = 0xFF;
+  if (on && !mine) T[kb] = 0xFFFF;
   __syncwarp();
-  const bool contended = on && T[kb] == 0xFF;
+  const bool contended = on && T[kb] == 0xFFFF;
   if (on && !contended) smem_rmw_add(col + kb, vre, vim);
   unsigned m = __ballot_sync(0xffffffffu, contended);
   while (m) {  // ascending lane = ascending source bin within a frame
@@ -63,12 +67,12 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
   float2* acc = smem;  // [F][AS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 3, c = lane & 7;
-  float2* xch = acc + F * AS + warp * (32 * XS);
+  float2* xch = acc + F * AS + warp * R256_WS;
   // after the second stage the exchange buffer holds the parked items and the tags, per frame g
   float2* sval = xch + g * SS;                                                    // [4][136]
   int* skey = reinterpret_cast<int*>(xch + 4 * SS) + g * SS;                      // [4][136]
-  unsigned char* tagA = reinterpret_cast<unsigned char*>(xch + 6 * SS) + g * SS;  // [4][136]
-  unsigned char* tagB = tagA + 4 * SS;
+  unsigned short* tagA = reinterpret_cast<unsigned short*>(xch + 6 * SS) + g * SS;  // [4][136], 16-bit: two bins per
+  unsigned short* tagB = tagA + 4 * SS;                                              // bank word instead of four
 
   for (int i = threadIdx.x; i < F * AS; i += blockDim.x) acc[i] = make_float2(0.f, 0.f);
   const bool c0 = c == 0;
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
       if (fl0 >= nf) break;
       const int fl = fl0 + g;
       const bool live = fl < nf;  // frames past the end compute on zeros; their columns are never stored
-      float2* col = acc + fl * AS;
+      float2* col = acc + fl * AS + 8 * (fl & 1);
       float2* colB = (MODE == 1) ? col + 4 * AS : nullptr;  // (a column past nf is written but never stored)
       float2 v[32];
       {
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
           cur.vre = sv.x;
           cur.vim = sv.y;
         }
-        if (cur.kb >= 0) tagA[cur.kb] = (unsigned char)lane;
+        if (cur.kb >= 0) tagA[cur.kb] = (unsigned short)lane;
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 17; ++i) {
@@ -217,12 +221,12 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
             nxt.vre = sv.x;
             nxt.vim = sv.y;
           }
-          unsigned char* T = (i & 1) ? tagB : tagA;
-          unsigned char* Tn = (i & 1) ? tagA : tagB;
+          unsigned short* T = (i & 1) ? tagB : tagA;
+          unsigned short* Tn = (i & 1) ? tagA : tagB;
           const bool on = cur.kb >= 0;
           float2* slot = col + (on ? cur.kb : 0);  // read with the tag: the two shared-memory latencies overlap
           float2 t = *slot;
-          const bool mine = !on || T[cur.kb] == (unsigned char)lane;
+          const bool mine = !on || T[cur.kb] == (unsigned short)lane;
           if (__all_sync(0xffffffffu, mine)) {
             if (on) {
               t.x += cur.vre;
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
           } else {
             r256_collision(col, T, cur.kb, cur.vre, cur.vim, mine, lane);
           }
-          if (i < 16 && nxt.kb >= 0) Tn[nxt.kb] = (unsigned char)lane;
+          if (i < 16 && nxt.kb >= 0) Tn[nxt.kb] = (unsigned short)lane;
           __syncwarp();
           cur = nxt;
         }
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
     {
       constexpr int RG = NW * 32 / F;
       const int fr = threadIdx.x % F, vv = threadIdx.x / F;
-      float2* a = acc + fr * AS + vv;
+      float2* a = acc + fr * AS + 8 * (fr & 1) + vv;
       float2* gp = P.out + ((size_t)ch * 129 + vv) * P.n_frames + tf0 + fr;
       const size_t gstep = (size_t)RG * P.n_frames;
       const bool ok = fr < nf;
@@ -274,7 +278,7 @@ static ssq_status stft_r256_launch_f(ssq_ctx* ctx, StftParams& P, bool* done) {
   Q.total_tiles = Q.tiles_per_channel * P.channels;
   if (Q.total_tiles > (int64_t)0x7ff00000) return SSQ_OK;
   *done = true;
-  const size_t smem = ((size_t)F * R256_AS + (size_t)NW * 32 * R1K_XS) * sizeof(float2);
+  const size_t smem = ((size_t)F * R256_AS + (size_t)NW * R256_WS) * sizeof(float2);
   const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx->num_sms * (F == 32 ? 3 : 4));
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
   void (*k)(const StftParams);
