@@ -194,9 +194,11 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_h32_kernel(const I
 // ------------------------------------------------------------------------------------
 #define I32T_AS 289  // tile row stride (float2): odd -> conflict-free transposed tile load; 578 floats >= 512
 
-template <bool HOP32>  // hop == 32: shifts instead of integer divisions in the gather
-__global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const Istft32Params P) {
-  constexpr int N = 512, AS = I32T_AS, F = 32;
+// NW warps per CTA, tile = 4 NW frames: 8 warps x 32 frames (2 CTAs per SM) or 4 warps x 16 frames (4 CTAs per SM: the
+// same 16 warps, but four independent CTAs interleave their load and transform phases and the barrier domain halves)
+template <bool HOP32, int NW>  // hop == 32: shifts instead of integer divisions in the gather
+__global__ void __launch_bounds__(NW * 32, 16 / NW) istft512_tile_kernel(const Istft32Params P) {
+  constexpr int N = 512, AS = I32T_AS, F = 4 * NW;
   extern __shared__ float2 smem[];
   float2* tw2tab = smem;      // [8][9]
   float2* S = smem + 72;      // [32][AS]
@@ -231,18 +233,20 @@ __global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_tile_kernel(const 
     const int ch = (int)(tile / P.runs_per_channel);
     const int64_t f0 = (tile % P.runs_per_channel) * F;
     const int nf = (int)min((int64_t)F, P.n_use - f0);
-    // ---- tile load: warp -> rows warp + 8 i, lane -> frame (256 B per row) -------------------------
+    // ---- tile load: 8 rows per step; lane -> frame (F = 32: one row per warp, 256 B; F = 16: two rows per warp) ----
     {
-      const float2* g = P.Sx + ((size_t)ch * 257 + warp) * P.n_frames + f0 + lane;
+      const int fr = lane & (F - 1), rsub = (NW == 8) ? 0 : (lane >> 4);
+      const int r0 = (NW == 8) ? warp : 2 * warp + rsub;
+      const float2* g = P.Sx + ((size_t)ch * 257 + r0) * P.n_frames + f0 + fr;
       const size_t gstep = (size_t)8 * P.n_frames;
-      float2* s = S + lane * AS + warp;
-      const bool ok = lane < nf;
+      float2* s = S + fr * AS + r0;
+      const bool ok = fr < nf;
 #pragma unroll 8
       for (int it = 0; it < 32; ++it) {  // (all 32 loads in flight at once measured slower: 11.05 vs 10.43 ms)
         s[8 * it] = ok ? __ldg(g) : make_float2(0.f, 0.f);
         g += gstep;
       }
-      if (warp == 0) s[256] = ok ? __ldg(g) : make_float2(0.f, 0.f);
+      if (r0 == 0) s[256] = ok ? __ldg(g) : make_float2(0.f, 0.f);
     }
     __syncthreads();
     // ---- transforms: warp w owns frames 4w .. 4w+3 (two packed pairs) --------------------------------
