@@ -13,8 +13,13 @@ against the Rust binary itself is UNPINNED.  What *is* pinned:
 
 * the restatement agrees with the vendored upstream `old/ssqueezepy`
   (imported in the build container) wherever the two implementations must
-  coincide (odd n_fft, fs=1, modulated=False) -- see
-  `tests/golden/make_golden.py`, which commits those vectors;
+  coincide -- vectors committed by `tests/golden/make_golden.py`:
+  odd n_fft, fs=1, modulated=False (`upstream_odd.npz`: Sx, dSx, Tx, istft to
+  1e-12); the BENCHMARK geometry n_fft=512, hop=32 on every frame that touches
+  no padding, via upstream run on the one-sample-shifted signal
+  (`upstream_even512.npz`: 4e-16); the CWT core and phase transform
+  (`upstream_cwt.npz`: all gmw rows 3e-15, morlet rows away from Nyquist 1e-8);
+  the admissibility constants (`upstream_adm.npz`);
 * every shape/dtype expectation of the reference smoke scripts
   (`tests/stft_test.py:137-151`, `tests/stft_ssq_test.py:132-152`,
   `tests/cwt_test.py:19-57`, `tests/ssq_cwt_test.py:19-57,410-419`).
