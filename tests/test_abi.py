@@ -80,3 +80,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".inl")):
                 s = open(os.path.join(dp, f)).read()
                 assert "oracle" not in s.replace("no Python/NumPy fallback", ""), f"{f} mentions the oracle"
+
+
+def test_host_only_entry_points_without_a_gpu():
+    """Entry points that need no device: the admissibility integral (host math, double) against the oracle's
+    quadrature, the shape queries and the default scales against the oracle."""
+    import ctypes as C
+    import numpy as np
+    from oracle import ssq_oracle as O
+    from ssqueeze_rs_b200 import _lib
+    lib = _lib.load()
+    for wid, name in ((0, "gmw"), (1, "morlet")):
+        out = C.c_double(0.0)
+        assert lib.ssq_cwt_admissibility(wid, C.addressof(out)) == 0
+        assert np.isclose(out.value, O.adm_ssq(name), rtol=1e-9), (name, out.value)
+    nf, nt = C.c_int64(), C.c_int64()
+    assert lib.ssq_stft_shape(1000, 256, 64, C.byref(nf), C.byref(nt)) == 0
+    assert (nf.value, nt.value) == (129, 16)  # tests/stft_test.py:137-151 of the reference
+    for n, nv in ((1000, 32), (1 << 20, 32), (4097, 16)):
+        ns = lib.ssq_cwt_default_scales(n, nv, 0, C.c_void_p(0))
+        sc = np.empty(ns)
+        lib.ssq_cwt_default_scales(n, nv, 0, C.c_void_p(sc.ctypes.data))
+        so = O.generate_log_scales(n, nv)
+        assert len(so) == ns and np.allclose(sc, so, rtol=1e-13)
