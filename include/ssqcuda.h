@@ -170,6 +170,12 @@ ssq_status ssq_cwt_admissibility(int wavelet, double* css);
 ssq_status ssq_issq_cwt_f64(ssq_ctx* ctx, const double* Tx, int64_t ns, int64_t n, int wavelet,
                             const double* scales, double* x);
 
+/* `issq_cwt` with curve bands (old/ssqueezepy/_ssq_cwt.py:313-402): component c of column j sums Re Tx over the rows
+ * cc[j][c] - cw[j][c] .. cc[j][c] + cw[j][c] (clipped; cc == -1: no curve at that column); the last output row is
+ * the residual (rows no band covers).  cc, cw: int32 [n][K], 1 <= K <= 16.  x: float64 [K + 1][n]. */
+ssq_status ssq_issq_cwt_components_f64(ssq_ctx* ctx, const double* Tx, int64_t ns, int64_t n, int wavelet,
+                                       const double* scales, const int* cc, const int* cw, int K, double* x);
+
 /* ---- batched throughput path (device buffers, fp32 / complex64) ---------- */
 /* replaces the per-channel Python loop around `_rs.ssq_stft`
  * (tests/stft_ssq_test.py:230-251).  d_x: [channels, n] fp32 with row stride

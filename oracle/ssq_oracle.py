@@ -513,14 +513,39 @@ def adm_ssq(wavelet="gmw"):
     return quad(f, 1e-12, 60.0, points=pts, epsabs=0.0, epsrel=1e-13, limit=2000)[0]
 
 
-def issq_cwt(Tx, wavelet="gmw", scales=None):
-    """old/ssqueezepy/_ssq_cwt.py:313-378 (full inversion) in the reference's framing: the log-step `const`
-    upstream bakes into Tx is applied here (the reference's ssqueeze omits it, ssq_cwt.rs:116-222)."""
+def invert_components(Tx, cc, cw):
+    """old/ssqueezepy/_ssq_cwt.py:380-402, restated: per component the rows cc-cw .. cc+cw of every column
+    (clipped to [0, n_rows]; cc == -1: none), each from the original Tx; last row: what no band covers."""
+    Tx = np.asarray(Tx)
+    n_rows, n = Tx.shape
+    cc = np.asarray(cc).reshape(n, -1).astype(np.int64)
+    cw = np.asarray(cw).reshape(n, -1).astype(np.int64)
+    K = cc.shape[1]
+    x = np.zeros((K + 1, n))
+    rest = Tx.real.copy()
+    for c in range(K):
+        upper = np.clip(cc[:, c] + cw[:, c], 0, n_rows)
+        lower = np.clip(cc[:, c] - cw[:, c], 0, n_rows)
+        upper[cc[:, c] == -1] = 0
+        lower[cc[:, c] == -1] = 1
+        for m in range(n):
+            sl = slice(lower[m], upper[m] + 1)
+            x[c, m] = Tx.real[sl, m].sum()
+            rest[sl, m] = 0.0
+    x[K] = rest.sum(axis=0)
+    return x
+
+
+def issq_cwt(Tx, wavelet="gmw", scales=None, cc=None, cw=None):
+    """old/ssqueezepy/_ssq_cwt.py:313-378 in the reference's framing: the log-step `const` upstream bakes into
+    Tx is applied here (the reference's ssqueeze omits it, ssq_cwt.rs:116-222)."""
     Tx = np.asarray(Tx, dtype=np.complex128)
     if scales is None:
         raise ValueError("Scales must be provided")
     scales = np.asarray(scales, dtype=np.float64)
     dj = math.log(scales[1] / scales[0]) if (len(scales) > 1 and scales[1] > scales[0]) else 0.1
+    if cc is not None:
+        return invert_components(Tx, cc, cw) * (2.0 / adm_ssq(wavelet)) * dj
     x = np.zeros(Tx.shape[1])
     for i in range(Tx.shape[0]):
         x += Tx[i].real

@@ -269,10 +269,12 @@ def adm_ssq(wavelet="gmw"):
     return out.value
 
 
-def issq_cwt(Tx, wavelet="gmw", scales=None):
-    """Full inversion of `ssq_cwt` (spec old/ssqueezepy/_ssq_cwt.py:313-378; absent from the reference crate):
+def issq_cwt(Tx, wavelet="gmw", scales=None, cc=None, cw=None):
+    """Inversion of `ssq_cwt` (spec old/ssqueezepy/_ssq_cwt.py:313-402; absent from the reference crate):
     x = (2/Css) ln(scales[1]/scales[0]) sum_k Re Tx[k].  `scales` are the ones `ssq_cwt` used; the log-step
-    factor is upstream's `const`, which the reference's ssqueeze leaves out of Tx (ssq_cwt.rs:116-222)."""
+    factor is upstream's `const`, which the reference's ssqueeze leaves out of Tx (ssq_cwt.rs:116-222).
+    `cc`, `cw` (int arrays [n] or [n, K]: centre row and half-width of K curve bands per column, cc == -1: no
+    curve) select the component inversion: returns [K + 1, n], the last row being the residual."""
     if not isinstance(Tx, np.ndarray) or Tx.ndim != 2 or Tx.dtype != np.complex128:
         raise TypeError("argument 'Tx': expected a 2-D numpy.ndarray of complex128")
     if scales is None:
@@ -280,9 +282,22 @@ def issq_cwt(Tx, wavelet="gmw", scales=None):
     sc = _f64_1d(scales, "scales")
     Tx = np.ascontiguousarray(Tx)
     ns, n = Tx.shape
-    x = np.empty(n, dtype=np.float64)
     ctx = default_context()
-    st = load().ssq_issq_cwt_f64(ctx.handle, _ptr(Tx), ns, n, 1 if _str(wavelet, "wavelet") == "morlet" else 0,
-                                 _ptr(sc), _ptr(x))
+    wid = 1 if _str(wavelet, "wavelet") == "morlet" else 0
+    if (cc is None) != (cw is None):
+        raise ValueError("cc and cw go together")
+    if cc is not None:
+        cc = np.ascontiguousarray(np.asarray(cc).reshape(n, -1), dtype=np.int32)
+        cw = np.ascontiguousarray(np.asarray(cw).reshape(n, -1), dtype=np.int32)
+        if cc.shape != cw.shape:
+            raise ValueError("cc and cw must have the same shape")
+        K = cc.shape[1]
+        x = np.empty((K + 1, n), dtype=np.float64)
+        st = load().ssq_issq_cwt_components_f64(ctx.handle, _ptr(Tx), ns, n, wid, _ptr(sc), _ptr(cc), _ptr(cw), K,
+                                                _ptr(x))
+        raise_status(st, ctx.handle)
+        return x
+    x = np.empty(n, dtype=np.float64)
+    st = load().ssq_issq_cwt_f64(ctx.handle, _ptr(Tx), ns, n, wid, _ptr(sc), _ptr(x))
     raise_status(st, ctx.handle)
     return x

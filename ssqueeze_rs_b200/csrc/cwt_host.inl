@@ -527,3 +527,50 @@ extern "C" ssq_status ssq_issq_cwt_f64(ssq_ctx* ctx, const double* Tx, int64_t n
   SSQ_TRY(ssq_issq_cwt_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, ns, n, wavelet, scales, (float*)ctx->ws_out.p));
   return download_f32_as_f64(ctx, ctx->ws_out.p, (size_t)n, x);
 }
+
+// issq_cwt with curve bands (old/ssqueezepy/_ssq_cwt.py:313-402): cc / cw int32 [n][K] (centre row and half-width per
+// column and component; cc == -1: no curve at that column).  x: [K + 1][n], the last row is the residual.
+extern "C" ssq_status ssq_issq_cwt_components_f64(ssq_ctx* ctx, const double* Tx, int64_t ns, int64_t n, int wavelet,
+                                                  const double* scales, const int* cc, const int* cw, int K,
+                                                  double* x) {
+  if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (!Tx || !x || !cc || !cw) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
+  if (!scales) return ssq_fail(ctx, SSQ_EINVAL, "Scales must be provided");
+  if (ns < 1 || n < 1) return ssq_fail(ctx, SSQ_EINVAL, "issq_cwt: empty Tx");
+  if (K < 1 || K > SSQ_MAX_COMPONENTS)
+    return ssq_fail(ctx, SSQ_EUNSUPPORTED, "issq_cwt: %d components (1..%d supported)", K, SSQ_MAX_COMPONENTS);
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // row bands per column, clipped as upstream does (:388-394): [lower, upper] inclusive, empty where cc == -1
+  std::vector<int> lo((size_t)n * K), hi((size_t)n * K);
+  for (int64_t j = 0; j < n; ++j)
+    for (int c = 0; c < K; ++c) {
+      const int64_t ce = cc[j * K + c], wi = cw[j * K + c];
+      int64_t u = std::min<int64_t>(std::max<int64_t>(ce + wi, 0), ns);
+      int64_t l = std::min<int64_t>(std::max<int64_t>(ce - wi, 0), ns);
+      if (ce == -1) {
+        u = 0;
+        l = 1;
+      }
+      lo[(size_t)j * K + c] = (int)l;
+      hi[(size_t)j * K + c] = (int)u;  // the slice [l, u + 1) of upstream; rows >= ns do not exist
+    }
+  const double css = ssqhost::admissibility_ssq(wavelet == SSQ_WAVELET_MORLET);
+  const double dj = (ns > 1 && scales[1] > scales[0]) ? std::log(scales[1] / scales[0]) : 0.1;
+  const size_t cnt = (size_t)ns * n;
+  SSQ_TRY(upload_f64_as_f32(ctx, Tx, cnt * 2, ctx->ws_in));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, (size_t)2 * n * K * sizeof(int)));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, (size_t)(K + 1) * n * sizeof(float)));
+  int* d_lo = (int*)ctx->ws_aux0.p;
+  int* d_hi = d_lo + (size_t)n * K;
+  SSQ_CUDA_TRY(ctx, cudaMemcpyAsync(d_lo, lo.data(), lo.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  SSQ_CUDA_TRY(ctx, cudaMemcpyAsync(d_hi, hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  issq_cwt_components_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+      (const float2*)ctx->ws_in.p, (int)ns, n, K, d_lo, d_hi, (float)((2.0 / css) * dj), (float*)ctx->ws_out.p);
+  SSQ_TRY(ssq_check_launch(ctx, "issq_cwt_components_kernel"));
+  ctx->last_kernel = "issq_cwt_components_kernel";
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->ev_valid = true;
+  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // lo / hi staging vectors go out of scope
+  return download_f32_as_f64(ctx, ctx->ws_out.p, (size_t)(K + 1) * n, x);
+}

@@ -22,6 +22,8 @@
   signal one sample earlier than the Rust code for even n_fft (pad n_fft/2 against (n_fft-1)/2,
   stft_utils.rs:19-49), so upstream run on x[1:] yields, on every frame that touches no padding, exactly
   the Rust frames of x.  Columns [j0, j1) of upstream's Sx, dSx and Tx are stored.
+* `upstream_components.npz` -- upstream `_invert_components` (`_ssq_cwt.py:380-402`: the curve-band inversion of
+  `issq_cwt`) on a random Tx with three bands (one with gaps, one random incl. out-of-range and -1 centres).
 * `upstream_cwt.npz` -- upstream `cwt(..., derivative=True)` and `phase_cwt` for an even N whose padded
   length is the same in both code bases (N=600 -> 1024), explicit scales, l1 norm, reflect padding.
   The Rust wavelets equal upstream's up to one constant each (`*_ratio`), so Wx/dWx must agree to
@@ -128,6 +130,20 @@ def upstream_even512():
     return out
 
 
+def upstream_components():
+    from ssqueezepy._ssq_cwt import _invert_components
+    rng = np.random.default_rng(20261021)
+    n_rows, n = 40, 300
+    Tx = rng.standard_normal((n_rows, n)) + 1j * rng.standard_normal((n_rows, n))
+    cc = np.stack([10 + np.round(3 * np.sin(np.arange(n) / 20)).astype(int), np.full(n, 28),
+                   rng.integers(-1, n_rows + 3, n)], axis=1)
+    cc[50:60, 0] = -1
+    cw = np.stack([np.full(n, 3), np.full(n, 5), rng.integers(0, 4, n)], axis=1)
+    x = _invert_components(Tx, cc.astype("int32"), cw.astype("int32"))
+    assert np.abs(O.invert_components(Tx, cc, cw) - x).max() < 1e-12, "oracle != upstream"
+    return dict(Tx=Tx, cc=cc.astype(np.int32), cw=cw.astype(np.int32), x=x)
+
+
 def upstream_cwt():
     import ssqueezepy as S
     from ssqueezepy import Wavelet
@@ -153,10 +169,11 @@ def upstream_cwt():
 
 
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "upstream_components.npz"), **upstream_components())
     np.savez_compressed(os.path.join(HERE, "upstream_even512.npz"), **upstream_even512())
     np.savez_compressed(os.path.join(HERE, "upstream_cwt.npz"), **upstream_cwt())
     np.savez_compressed(os.path.join(HERE, "upstream_adm.npz"), **upstream_adm())
     np.savez_compressed(os.path.join(HERE, "upstream_odd.npz"), **upstream_cases())
     np.savez_compressed(os.path.join(HERE, "readme_cases.npz"), **readme_cases())
-    for f in ("upstream_even512.npz", "upstream_cwt.npz", "upstream_adm.npz", "upstream_odd.npz", "readme_cases.npz"):
+    for f in ("upstream_components.npz", "upstream_even512.npz", "upstream_cwt.npz", "upstream_adm.npz", "upstream_odd.npz", "readme_cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -190,3 +190,17 @@ def test_oracle_benchmark_geometry_pinned_to_upstream():
         ref = z[key]
         assert np.abs(got[:, j0:j1] - ref).max() < 1e-12 * np.abs(ref).max(), key
     assert np.allclose(sf, z["ssq_freqs"], rtol=0, atol=1e-15)
+
+
+def test_oracle_component_inversion_pinned_to_upstream():
+    """invert_components (the curve-band branch of issq_cwt) against upstream `_invert_components`
+    (old/ssqueezepy/_ssq_cwt.py:380-402; tests/golden/upstream_components.npz)."""
+    z = np.load(os.path.join(G, "upstream_components.npz"))
+    x = O.invert_components(z["Tx"], z["cc"], z["cw"])
+    assert x.shape == z["x"].shape == (4, 300)
+    assert np.abs(x - z["x"]).max() < 1e-12
+    # bands cover disjoint or overlapping rows; band sums plus residual exceed the plain sum only by the overlaps
+    sc = 2.0 ** np.linspace(1, 5, 40)
+    full = O.issq_cwt(z["Tx"], "gmw", sc)
+    comp = O.issq_cwt(z["Tx"], "gmw", sc, z["cc"], z["cw"])
+    assert comp.shape == (4, 300) and np.all(np.isfinite(comp)) and full.shape == (300,)

@@ -282,3 +282,23 @@ def test_full_size_round_trips_config3():
     colsum_T = Tx.sum(dim=1)
     rel_cs = float((colsum_T - colsum_W)[0, core].abs().mean() / colsum_W[0, core].abs().mean())
     assert rel_cs < 5e-2, rel_cs
+
+
+def test_issq_cwt_components():
+    """Curve-band inversion (old/ssqueezepy/_ssq_cwt.py:380-402) on the device against upstream's own output
+    (up to the admissibility / log-step factor) and against the oracle."""
+    rs = _rs()
+    z = np.load(os.path.join(G, "upstream_components.npz"))
+    Tx, cc, cw = z["Tx"], z["cc"], z["cw"]
+    sc = 2.0 ** np.linspace(1, 5, Tx.shape[0])
+    for wav in ("gmw", "morlet"):
+        x = rs.issq_cwt(Tx, wav, sc, cc, cw)
+        assert x.shape == (4, 300) and x.dtype == np.float64
+        f = (2.0 / rs.adm_ssq(wav)) * np.log(sc[1] / sc[0])
+        assert np.abs(x / f - z["x"]).max() < RTOL * np.abs(z["x"]).max(), wav
+        assert np.abs(x - O.issq_cwt(Tx, wav, sc, cc, cw)).max() < RTOL * np.abs(x).max(), wav
+    one = rs.issq_cwt(Tx, "gmw", sc, cc[:, 0], cw[:, 0])  # 1-D cc / cw: one band
+    assert one.shape == (2, 300)
+    assert np.abs(one[0] - rs.issq_cwt(Tx, "gmw", sc, cc, cw)[0]).max() == 0.0
+    with pytest.raises(ValueError):
+        rs.issq_cwt(Tx, "gmw", sc, cc)
