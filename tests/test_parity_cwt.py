@@ -302,3 +302,34 @@ def test_issq_cwt_components():
     assert np.abs(one[0] - rs.issq_cwt(Tx, "gmw", sc, cc, cw)[0]).max() == 0.0
     with pytest.raises(ValueError):
         rs.issq_cwt(Tx, "gmw", sc, cc)
+
+
+def test_cwt_tiny_and_ragged_inputs():
+    """Edge cases the reference accepts: N from 2 samples (pad_len 2 .. 64: single-pass FFT plans), odd lengths,
+    explicit scales, both wavelets, the squeezed transform with every option -- against the oracle."""
+    rs = _rs()
+    rng = np.random.default_rng(99)
+    sc = np.array([2.0, 4.0, 9.5])
+    for N in (2, 3, 4, 5, 8, 16, 33, 127, 1025):
+        x = rng.standard_normal(N)
+        for wav in ("gmw", "morlet"):
+            Wx, s, dWx = rs.cwt(x, wav, sc, fs=2.0, derivative=True)
+            Wo, so, dWo = O.cwt(x, wav, sc, fs=2.0, derivative=True)
+            assert Wx.shape == Wo.shape == (3, N), (N, wav)
+            # (+1e-30: psi-hat below the fp32 range is zero on the device, 1e-60 in the float64 oracle)
+            assert np.abs(Wx - Wo).max() <= RTOL * np.abs(Wo).max() + 1e-30, (N, wav)
+            assert np.abs(dWx - dWo).max() <= RTOL * np.abs(dWo).max() + 1e-30, (N, wav)
+        for kw in (dict(), dict(maprange="maximal"), dict(squeezing="lebesgue", maprange="maximal"),
+                   dict(flipud=False, maprange="maximal", ssq_freqs="linear")):
+            Tx, sf = rs.ssq_cwt(x, "gmw", sc, fs=2.0, **kw)
+            To, sfo = O.ssq_cwt(x, "gmw", sc, fs=2.0, **kw)
+            assert Tx.shape == To.shape == (3, N) and np.allclose(sf, sfo, rtol=1e-13), (N, kw)
+            bad = np.abs(Tx - To) > RTOL * np.abs(To).max() + 1e-7
+            assert bad.mean() <= 0.05, (N, kw, float(bad.mean()))
+    if True:  # default scales on short signals: ns = ceil((log2(N/2) - 1) nv) (cwt.rs:461-489); 0 scales for N <= 4
+        for N in (5, 8, 33):
+            x = rng.standard_normal(N)
+            Wx, s, _ = rs.cwt(x, "gmw", None, nv=4)
+            Wo, so, _ = O.cwt(x, "gmw", None, nv=4)
+            assert Wx.shape == Wo.shape and np.allclose(s, so, rtol=1e-13), N
+            assert np.abs(Wx - Wo).max() <= RTOL * np.abs(Wo).max() + 1e-30, N
