@@ -554,8 +554,8 @@ def issq_cwt(Tx, wavelet="gmw", scales=None, cc=None, cw=None):
 
 def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_mean=0.0,
          padtype="reflect", rpadded=False, l1_norm=True, exact_adm=False):
-    """cwt.rs:548-718.  Only the one-integral branch (:590-627, the default) is restated: the
-    two-integral branch needs FFTs of arbitrary length x_len and is not built (SSQ_EUNSUPPORTED)."""
+    """cwt.rs:548-718: the one-integral branch (:590-627, the default) and the two-integral branch (:629-712;
+    the device builds the latter for power-of-two x_len == Wx.shape[1] only)."""
     Wx = np.asarray(Wx, dtype=np.complex128)
     if scales is None:
         raise ValueError("Scales must be provided")  # cwt.rs:572-575
@@ -568,7 +568,17 @@ def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_me
     if x_length > n_times:
         raise IndexError("x_len > Wx.shape[1]: ndarray index out of bounds (panic) at cwt.rs:613")
     if not one_int:
-        raise NotImplementedError("two-integral icwt (cwt.rs:629-712) is not restated")
+        # cwt.rs:629-712: per scale FFT(Wx[i, :x_len]) * conj(psi-hat(scale xi)) -> IFFT; real part / x_len times
+        # 1/scale (l1) or 1/sqrt(scale)^2 (otherwise: the same number); summed, then * (2/adm) dj + x_mean
+        xi = xifn(1.0, x_length)
+        x = np.zeros(x_length)
+        for i in range(n_scales):
+            psih = generate_wavelet_fourier(xi, scales[i], wavelet)
+            tmp = np.fft.ifft(np.fft.fft(Wx[i, :x_length]) * np.conj(psih)) * x_length  # rustfft: unnormalised inverse
+            scale_norm = 1.0 / scales[i] if l1_norm else 1.0 / math.sqrt(scales[i]) ** 2
+            x += tmp.real * (1.0 / x_length) * scale_norm
+        dj = math.log(scales[1] / scales[0]) if (n_scales > 1 and scales[1] > scales[0]) else 0.1
+        return x * ((2.0 / adm) * dj) + x_mean
     dj = math.log(scales[1] / scales[0]) if (n_scales > 1 and scales[1] > scales[0]) else 0.1  # :595-599
     final_norm = (2.0 / adm) * dj
     norm = np.ones(n_scales) if l1_norm else 1.0 / np.sqrt(scales[:n_scales])                 # :606-610

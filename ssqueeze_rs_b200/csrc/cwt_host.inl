@@ -80,7 +80,7 @@ static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int
     const bool first = (i == skip), last = (i == pl.npass - 1);
     if (!first) P.load_mode = 0;
     if (!last) P.store_mode = 0;
-    P.in = cur_in;
+    P.in = first ? base.in : cur_in;  // load_mode 0 on the first pass reads base.in (two-integral icwt)
     float2* o = last ? base.out : ((i & 1) ? ws1 : ws0);
     P.out = o;
     const int R = 1 << P.r, T = 1 << P.log2T;
@@ -442,13 +442,74 @@ extern "C" ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_
   if (x_len > n_cols)
     return ssq_fail(ctx, SSQ_EPANIC, "x_len %lld > Wx.shape[1] %lld: index out of bounds in the reference (cwt.rs:613)",
                     (long long)x_len, (long long)n_cols);
-  if (!one_int)
-    return ssq_fail(ctx, SSQ_EUNSUPPORTED, "icwt: the two-integral branch (cwt.rs:629-712) is not built; use one_int=True");
   SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const double adm = (flags & SSQ_FLAG_ADM_EXACT) ? ssqhost::admissibility_ssq(wavelet == SSQ_WAVELET_MORLET)
                      : wavelet == SSQ_WAVELET_MORLET ? 0.776 : 1.0;                                 // cwt.rs:579-583
   const double dj = (ns > 1 && scales[1] > scales[0]) ? std::log(scales[1] / scales[0]) : 0.1;     // :595-599
   const double final_norm = (2.0 / adm) * dj;
+  if (!one_int) {
+    // Two-integral branch (cwt.rs:629-712): per scale FFT(Wx[i]) * conj(psi-hat_i) -> IFFT, real part / x_len /
+    // scale, summed over the scales.  By linearity the sum is taken in the frequency domain and ONE inverse
+    // transform follows.  The reference transforms rows of arbitrary length x_len (rustfft); here x_len must be
+    // a power of two equal to the row length (e.g. rpadded Wx).
+    int l2 = 0;
+    while (((int64_t)1 << l2) < x_len) ++l2;
+    if (x_len != n_cols || ((int64_t)1 << l2) != x_len || l2 < 1 || l2 > 27)
+      return ssq_fail(ctx, SSQ_EUNSUPPORTED,
+                      "icwt: the two-integral branch (cwt.rs:629-712) is built for x_len == Wx.shape[1] == 2^k only "
+                      "(got x_len %lld, %lld columns); use one_int=True", (long long)x_len, (long long)n_cols);
+    const int64_t L = x_len;
+    const FftPlanHost pl = fft_plan(l2);
+    const float2 *lo, *hi;
+    int tw_s;
+    SSQ_TRY(cwt_twiddles(ctx, l2, &lo, &hi, &tw_s));
+    std::vector<float> hs((size_t)ns);
+    for (int64_t i = 0; i < ns; ++i) hs[(size_t)i] = (float)scales[i];
+    SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, hs.size() * sizeof(float)));
+    SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>(ns, ((int64_t)1 << 30) / (L * 8)));
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft0, (size_t)ns * L * sizeof(float2)));
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft1, (size_t)2 * max_rows * L * sizeof(float2)));
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, (size_t)2 * L * sizeof(float2)));
+    float2* What = (float2*)ctx->ws_fft0.p;
+    float2* ws0 = (float2*)ctx->ws_fft1.p;
+    float2* ws1 = ws0 + (size_t)max_rows * L;
+    float2* S = (float2*)ctx->ws_aux0.p;
+    float2* S2 = S + L;
+    FftPass B;
+    memset(&B, 0, sizeof(B));
+    B.tw_lo = lo;
+    B.tw_hi = hi;
+    B.tw_s = tw_s;
+    const double K = cwt_denorm_constant(wavelet);
+    SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int64_t ch = 0; ch < channels; ++ch) {
+      B.sign = -1;
+      for (int64_t r0 = 0; r0 < ns; r0 += max_rows) {
+        const int rows = (int)std::min<int64_t>(max_rows, ns - r0);
+        B.in = (const float2*)d_Wx + ((size_t)ch * ns + r0) * L;
+        B.out = What + (size_t)r0 * L;
+        B.row0 = r0;
+        SSQ_TRY(fft_run(ctx, pl, B, rows, ws0, ws1));
+      }
+      icwt2_accum_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(
+          What, (int)ns, (int)L, (const float*)ctx->cwt_scales.p, wavelet == SSQ_WAVELET_MORLET ? SSQ_WAVELET_MORLET : SSQ_WAVELET_GMW, S);
+      SSQ_TRY(ssq_check_launch(ctx, "icwt2_accum_kernel"));
+      B.sign = +1;
+      B.in = S;
+      B.out = S2;
+      B.row0 = 0;
+      SSQ_TRY(fft_run(ctx, pl, B, 1, ws0, ws1));
+      icwt2_finalize_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(
+          S2, L, (float)(K * final_norm / (double)L), (float)x_mean, d_x + (size_t)ch * L);
+      SSQ_TRY(ssq_check_launch(ctx, "icwt2_finalize_kernel"));
+    }
+    ctx->last_kernel = "icwt2_accum_kernel";
+    SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ev_valid = true;
+    return SSQ_OK;
+  }
   std::vector<float> hn((size_t)ns);
   for (int64_t i = 0; i < ns; ++i)
     hn[(size_t)i] = (flags & SSQ_FLAG_L2_NORM) ? (float)(1.0 / std::sqrt(scales[i])) : 1.f;       // :606-610

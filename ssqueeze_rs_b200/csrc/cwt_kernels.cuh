@@ -547,3 +547,34 @@ __global__ void issq_cwt_components_kernel(const float2* __restrict__ Tx, int ns
   x[(size_t)K * n + j] = rest * scale;
 }
 
+// ------------------------------------------------------------------------------------
+// icwt, two-integral branch (cwt.rs:629-712) in the frequency domain:
+//   S[k] = sum_i FFT(Wx[i])[k] * psi-hat(scale_i xi_k) / scale_i   (psi-hat real; peak-normalised here, the constant
+//   goes into the final factor), then x = Re(IFFT(S)) * norm + x_mean.
+// ------------------------------------------------------------------------------------
+__global__ void icwt2_accum_kernel(const float2* __restrict__ What, int ns, int L, const float* __restrict__ scales,
+                                   int wavelet, float2* __restrict__ S) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= L) return;
+  // wavelets/base.rs:18-33: xi_k = 2 pi k / L up to and including the Nyquist bin, 2 pi (k - L) / L above
+  const float xi = 6.283185307179586f * (float)(k <= (L >> 1) ? k : k - L) / (float)L;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int i = 0; i < ns; ++i) {
+    const float sc = __ldg(scales + i);
+    const float ps = psihat(wavelet, sc * xi);
+    if (ps != 0.f) {
+      const float2 w = What[(size_t)i * L + k];
+      const float f = ps / sc;  // 1/scale for both norms (cwt.rs:684-688: 1/scale and 1/sqrt(scale)^2)
+      acc.x = fmaf(w.x, f, acc.x);
+      acc.y = fmaf(w.y, f, acc.y);
+    }
+  }
+  S[k] = acc;
+}
+
+__global__ void icwt2_finalize_kernel(const float2* __restrict__ s, int64_t L, float norm, float x_mean,
+                                      float* __restrict__ x) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < L) x[j] = fmaf(s[j].x, norm, x_mean);
+}
+

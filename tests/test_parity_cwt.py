@@ -333,3 +333,25 @@ def test_cwt_tiny_and_ragged_inputs():
             Wo, so, _ = O.cwt(x, "gmw", None, nv=4)
             assert Wx.shape == Wo.shape and np.allclose(s, so, rtol=1e-13), N
             assert np.abs(Wx - Wo).max() <= RTOL * np.abs(Wo).max() + 1e-30, N
+
+
+def test_icwt_two_integral_power_of_two():
+    """cwt.rs:629-712 (two-integral branch) on rpadded coefficients (row length 2^k) against the oracle; other
+    lengths are refused."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import SsqError
+    rng = np.random.default_rng(21)
+    for N, sc in ((3000, 2.0 ** np.linspace(1, 8, 30)), (700, 2.0 ** np.linspace(1, 6, 12)), (70000, 2.0 ** np.linspace(1, 12, 40))):
+        x = rng.standard_normal(N)
+        for wav in ("gmw", "morlet"):
+            for l1 in (True, False):
+                Wx, _, _ = rs.cwt(x, wav, sc, fs=1.0, rpadded=True, l1_norm=l1)
+                L = Wx.shape[1]
+                assert L & (L - 1) == 0
+                xr = rs.icwt(Wx, wav, sc, one_int=False, l1_norm=l1, x_mean=-0.5)
+                xo = O.icwt(Wx, wav, sc, one_int=False, l1_norm=l1, x_mean=-0.5)
+                assert xr.shape == (L,)
+                assert np.abs(xr - xo).max() < 2 * RTOL * np.abs(xo + 0.5).max(), (N, wav, l1)
+    Wx, _, _ = rs.cwt(rng.standard_normal(3000), "gmw", 2.0 ** np.linspace(1, 8, 30), fs=1.0)
+    with pytest.raises(SsqError):
+        rs.icwt(Wx, "gmw", 2.0 ** np.linspace(1, 8, 30), one_int=False)  # 3000 columns: not a power of two
