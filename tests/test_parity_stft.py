@@ -649,3 +649,25 @@ def test_fast_kernels_randomised_sweep():
             Sx, _ = rs.stft(x, n_fft, hop, win, kw["padtype"])
             So, _ = O.stft(x, n_fft, hop, win, kw["padtype"])
             assert rel(Sx, So) < RTOL, (case, n_fft, N, hop, wname)
+
+
+@pytest.mark.parametrize("hop,N", [(256, 40000), (100, 9000), (1, 1500), (1024, 30000), (1500, 20000), (32, 300)])
+def test_istft_1024(hop, N):
+    """n_fft=1024 inverse (register 32 x 32 FFT, packed frame pairs, gather overlap-add) against the oracle, both
+    window exponents, plus the round trip through the n_fft=1024 forward kernel."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    rng = np.random.default_rng(hop + 7)
+    x = rng.standard_normal(N)
+    win = np.hanning(1026)[1:-1].copy()
+    So, _ = O.stft(x, 1024, hop, win, "reflect")
+    So = So * (1 + 0.05 * rng.standard_normal(So.shape))
+    for wexp in (1, 0):
+        xr = rs.istft(So, win, n_fft=1024, hop_len=hop, N=N, win_exp=wexp)
+        assert "istft1024" in _lib.default_context().last_kernel_name()
+        xo = O.istft(So, win, n_fft=1024, hop_len=hop, N=N, win_exp=wexp)
+        assert np.abs(xr - xo).max() < RTOL * max(np.abs(xo).max(), 1e-30), (hop, wexp)
+    if hop <= 512:
+        Sx, _ = rs.stft(x, 1024, hop, win, "reflect")
+        xb = rs.istft(Sx, win, n_fft=1024, hop_len=hop, N=N)
+        assert np.abs(xb - x).max() < 1e-4 * np.abs(x).max(), hop
