@@ -11,6 +11,7 @@
 #include "stft_r256.cuh"
 #include "istft_h32.cuh"
 #include "istft_r1024.cuh"
+#include "istft_r256.cuh"
 #include "cwt_kernels.cuh"
 
 #include <algorithm>
@@ -528,6 +529,40 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
                                                       (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
     SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
     return SSQ_OK;
+  }
+
+  if (n_fft == 256 && !getenv("SSQ_NO_R256")) {
+    Istft32Params Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.Sx = (const float2*)d_Sx;
+    Q.channels = (int)channels;
+    Q.n_frames = n_frames;
+    Q.n_use = std::min<int64_t>(n_frames, max_hops);
+    Q.L = L;
+    Q.wa = T.wa;
+    Q.tw = T.tw;
+    Q.xacc = (float*)ctx->ws_misc.p;
+    Q.hop = hop;
+    constexpr int NW = 4, F = 32;
+    Q.run = F;
+    Q.runs_per_channel = (Q.n_use + F - 1) / F;
+    Q.total_runs = Q.runs_per_channel * channels;
+    if (Q.total_runs <= (int64_t)0x7ff00000 && (int64_t)(F - 1) * hop + 256 < ((int64_t)1 << 30)) {
+      const size_t smem = ((size_t)F * I256_AS + (size_t)NW * 32 * R1K_XS) * sizeof(float2);
+      const int grid = (int)std::min<int64_t>(Q.total_runs, (int64_t)ctx->num_sms * 3);
+      SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+      SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(istft256_tile_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      istft256_tile_kernel<NW><<<grid, NW * 32, smem, ctx->stream>>>(Q);
+      SSQ_TRY(ssq_check_launch(ctx, "istft256_tile_kernel"));
+      ctx->last_kernel = "istft256_tile_kernel";
+      SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+      ctx->ev_valid = true;
+      dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
+      istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
+                                                        (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+      SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
+      return SSQ_OK;
+    }
   }
 
   if (n_fft == 1024 && !getenv("SSQ_NO_R1024")) {

@@ -671,3 +671,25 @@ def test_istft_1024(hop, N):
         Sx, _ = rs.stft(x, 1024, hop, win, "reflect")
         xb = rs.istft(Sx, win, n_fft=1024, hop_len=hop, N=N)
         assert np.abs(xb - x).max() < 1e-4 * np.abs(x).max(), hop
+
+
+@pytest.mark.parametrize("hop,N", [(64, 40000), (17, 5000), (1, 900), (256, 30000), (300, 20000), (8, 100)])
+def test_istft_256(hop, N):
+    """n_fft=256 inverse (8 x 32 register FFT, four packed pairs of frames per warp) against the oracle, both window
+    exponents, plus the round trip through the n_fft=256 forward kernel."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    rng = np.random.default_rng(hop + 11)
+    x = rng.standard_normal(N)
+    win = np.hanning(258)[1:-1].copy()
+    So, _ = O.stft(x, 256, hop, win, "reflect")
+    So = So * (1 + 0.05 * rng.standard_normal(So.shape))
+    for wexp in (1, 0):
+        xr = rs.istft(So, win, n_fft=256, hop_len=hop, N=N, win_exp=wexp)
+        assert "istft256" in _lib.default_context().last_kernel_name()
+        xo = O.istft(So, win, n_fft=256, hop_len=hop, N=N, win_exp=wexp)
+        assert np.abs(xr - xo).max() < RTOL * max(np.abs(xo).max(), 1e-30), (hop, wexp)
+    if hop <= 128:
+        Sx, _ = rs.stft(x, 256, hop, win, "reflect")
+        xb = rs.istft(Sx, win, n_fft=256, hop_len=hop, N=N)
+        assert np.abs(xb - x).max() < 1e-4 * np.abs(x).max(), hop
