@@ -9,7 +9,8 @@
 #include "istft_h32.cuh"
 #include "stft_r1024.cuh"
 
-#define I1K_AS 515  // tile row stride (float2): odd -> conflict-free transposed load; 1030 floats >= 1024 samples
+#define I1K_AS 514  // tile row stride (float2): 2 AS = 4 mod 32 -> the transposed load (8 frames x 4 rows per warp step) is
+                    // bank-conflict free; 1028 floats >= 1024 samples
 
 template <int NW>  // F = 2 NW frames per tile
 __global__ void __launch_bounds__(NW * 32, 3) istft1024_tile_kernel(const Istft32Params P) {
