@@ -111,11 +111,17 @@ __global__ void __launch_bounds__(NW * 32, 3) istft1024_tile_kernel(const Istft3
       float* xo = P.xacc + (size_t)ch * P.L + f0 * hop;
       const int64_t room = P.L - f0 * hop;
       const float* Sf = reinterpret_cast<const float*>(S);
+      const float inv_hop = 1.f / (float)hop;
+      const int step = 2 * AS - hop;
       for (int p = threadIdx.x; p < span; p += blockDim.x) {
-        const int fhi = min(nf - 1, p / hop);
-        const int flo = p < N ? 0 : (p - N + hop) / hop;  // ceil((p - N + 1) / hop)
+        const int fhi = min(nf - 1, ssq_fast_div(p, hop, inv_hop));
+        const int flo = p < N ? 0 : ssq_fast_div(p - N + hop, hop, inv_hop);  // ceil((p - N + 1) / hop)
+        const float* src = Sf + flo * step + p;
         float acc = 0.f;
-        for (int f = flo; f <= fhi; ++f) acc += Sf[f * (2 * AS) + (p - hop * f)];
+        for (int f = flo; f <= fhi; ++f) {
+          acc += *src;
+          src += step;
+        }
         if (p < room && flo <= fhi) atomicAdd(xo + p, acc);
       }
     }

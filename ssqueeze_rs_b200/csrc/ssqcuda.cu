@@ -480,7 +480,8 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
   SSQ_TRY(devbuf_reserve(ctx, ctx->ws_misc, (size_t)channels * L * sizeof(float)));
   SSQ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_misc.p, 0, (size_t)channels * L * sizeof(float), ctx->stream));
 
-  if (n_fft == 512 && !getenv("SSQ_NO_H32") && (hop == 32 || !getenv("SSQ_ISTFT_RUNS"))) {
+  if (n_fft == 512 && !getenv("SSQ_NO_H32") && (hop == 32 || !getenv("SSQ_ISTFT_RUNS")) &&
+      (int64_t)31 * hop + 512 < ((int64_t)1 << 22)) {  // tile span inside the range of ssq_fast_div
     Istft32Params Q;
     memset(&Q, 0, sizeof(Q));
     Q.Sx = (const float2*)d_Sx;
@@ -547,7 +548,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
     Q.run = F;
     Q.runs_per_channel = (Q.n_use + F - 1) / F;
     Q.total_runs = Q.runs_per_channel * channels;
-    if (Q.total_runs <= (int64_t)0x7ff00000 && (int64_t)(F - 1) * hop + 256 < ((int64_t)1 << 30)) {
+    if (Q.total_runs <= (int64_t)0x7ff00000 && (int64_t)(F - 1) * hop + 256 < ((int64_t)1 << 22)) {
       const size_t smem = ((size_t)F * I256_AS + (size_t)NW * 32 * R1K_XS) * sizeof(float2);
       const int grid = (int)std::min<int64_t>(Q.total_runs, (int64_t)ctx->num_sms * 3);
       SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -581,7 +582,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
     Q.run = F;
     Q.runs_per_channel = (Q.n_use + F - 1) / F;
     Q.total_runs = Q.runs_per_channel * channels;
-    if (Q.total_runs <= (int64_t)0x7ff00000 && (int64_t)(F - 1) * hop + 1024 < ((int64_t)1 << 30)) {
+    if (Q.total_runs <= (int64_t)0x7ff00000 && (int64_t)(F - 1) * hop + 1024 < ((int64_t)1 << 22)) {
       const size_t smem = ((size_t)F * I1K_AS + (size_t)NW * 32 * R1K_XS) * sizeof(float2);
       const int grid = (int)std::min<int64_t>(Q.total_runs, (int64_t)ctx->num_sms * 3);
       SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
