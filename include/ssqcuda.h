@@ -75,8 +75,10 @@ enum {
 };
 
 /* ---- library / context ------------------------------------------------- */
-/* replaces hello_from_bin (lib.rs:16-19): static identification string */
+/* library identification string */
 const char* ssq_version(void);
+/* replaces hello_from_bin (lib.rs:16-19): the reference's greeting, verbatim */
+const char* ssq_hello_from_bin(void);
 int ssq_device_count(void);
 ssq_status ssq_ctx_create(int device, ssq_ctx** out);
 void ssq_ctx_destroy(ssq_ctx* ctx);
@@ -84,6 +86,11 @@ const char* ssq_last_error(const ssq_ctx* ctx);
 /* borrow a caller-owned cudaStream_t (NULL restores the context's own stream) */
 ssq_status ssq_ctx_set_stream(ssq_ctx* ctx, void* cuda_stream);
 ssq_status ssq_ctx_synchronize(ssq_ctx* ctx);
+/* kernel-selection switches for measurements and cross-checks; none changes results beyond
+ * fp32 rounding.  Every option is seeded once, at ssq_ctx_create, from the environment variable SSQ_<NAME>.
+ * names: no_h32r, h32r_nw (4|8), no_r1024, no_r256, istft_nw (4|8), no_fft128, fft128_tc (32|64),
+ * no_cwt_prune, no_cwt_fused, cwt_ws_mb. */
+ssq_status ssq_ctx_set_option(ssq_ctx* ctx, const char* name, int64_t value);
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 uint64_t ssq_ctx_launch_count(const ssq_ctx* ctx);
 /* device-time of the most recent batch call's dominant kernel, measured with
@@ -110,15 +117,17 @@ ssq_status ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n, int n_fft, int
                         double* Sx, double* freqs);
 
 /* replaces the body of `ssq_stft` (ssq_stft.rs:74-313).  n_fft<=0: min(n,512)
- * (:92); win_len<=0: win_n (:93); gamma<0 or NaN: 10*EPS64 (:258-261).
+ * (:92); win_len<=0: win_n (:93); gamma NaN ("not given"): 10*EPS64 (:258-261), gamma < 0: nothing is gated (:23).
  * Tx: complex128 [n_freqs, n_frames]; ssq_freqs: float64 [n_freqs].
- * Optional (may be NULL): Sx, dSx complex128 same shape; w float64 same shape
- * (+inf where gated). */
+ * Optional diagnostics (may be NULL), written by the SAME kernel that produces Tx (a compile-time variant
+ * with the extra stores): Sx, dSx complex128 same shape; w float64 same shape (+inf where gated);
+ * kb int32 same shape: the destination bin of every (source bin, frame), -1 where gated -- what the
+ * parity tests compare with the reference's arg-min (ssq_stft.rs:276-301). */
 ssq_status ssq_ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n,
                             const double* window, int64_t win_n, int n_fft, int win_len,
                             int hop, double fs, int padtype, int squeezing, double gamma,
                             unsigned flags, double* Tx, double* ssq_freqs,
-                            double* Sx, double* dSx, double* w);
+                            double* Sx, double* dSx, double* w, int32_t* kb);
 
 /* `istft`: absent from the Rust crate (lib.rs:25-32) but named by the north
  * star; specified from old/ssqueezepy/_stft.py:184-256 in the Rust framing
@@ -187,6 +196,14 @@ ssq_status ssq_ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channe
                                   int64_t x_stride, const double* window, int64_t win_n,
                                   int n_fft, int hop, double fs, int padtype, int squeezing,
                                   double gamma, unsigned flags, float* d_Tx);
+/* diagnostic twin (parity tests, bench.py's parity leg): the same kernel selection; any non-NULL d_Sx / d_dSx
+ * (complex64), d_w (fp32, Hz, +inf where gated), d_kb (int32 destination bin per (source bin, frame), -1 gated),
+ * each [channels, n_freqs, n_frames], is written by the kernel that produces d_Tx (compile-time variant). */
+ssq_status ssq_ssq_stft_batch_diag_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                       int64_t x_stride, const double* window, int64_t win_n,
+                                       int n_fft, int hop, double fs, int padtype, int squeezing,
+                                       double gamma, unsigned flags, float* d_Tx, float* d_Sx, float* d_dSx,
+                                       float* d_w, int32_t* d_kb);
 /* same framing, output Sx (complex64 [channels, n_freqs, n_frames]); the
  * window is used as given when win_n >= n_fft (first n_fft taps, stft_utils.rs:8) */
 ssq_status ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,

@@ -36,12 +36,14 @@ P_dbl = C.POINTER(C.c_double)
 # name -> (restype, argtypes); every symbol include/ssqcuda.h declares
 SIGNATURES = {
     "ssq_version": (C.c_char_p, []),
+    "ssq_hello_from_bin": (C.c_char_p, []),
     "ssq_device_count": (c_int, []),
     "ssq_ctx_create": (c_int, [c_int, C.POINTER(c_vp)]),
     "ssq_ctx_destroy": (None, [c_vp]),
     "ssq_last_error": (C.c_char_p, [c_vp]),
     "ssq_ctx_set_stream": (c_int, [c_vp, c_vp]),
     "ssq_ctx_synchronize": (c_int, [c_vp]),
+    "ssq_ctx_set_option": (c_int, [c_vp, C.c_char_p, c_i64]),
     "ssq_ctx_launch_count": (C.c_uint64, [c_vp]),
     "ssq_ctx_last_kernel_ms": (C.c_float, [c_vp]),
     "ssq_ctx_last_kernel_name": (C.c_char_p, [c_vp]),
@@ -50,7 +52,7 @@ SIGNATURES = {
     "ssq_cwt_default_scales": (c_i64, [c_i64, c_int, c_int, c_vp]),
     "ssq_stft_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp]),
     "ssq_ssq_stft_f64": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_dbl, c_int, c_int,
-                                 c_dbl, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                 c_dbl, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ssq_istft_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int, c_vp]),
     "ssq_issq_stft_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_vp]),
     "ssq_cwt_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_dbl, c_int, c_u32, c_vp, c_vp]),
@@ -64,6 +66,8 @@ SIGNATURES = {
     "ssq_icwt_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_int, c_i64, c_dbl, c_u32, c_vp]),
     "ssq_ssq_stft_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl,
                                        c_int, c_int, c_dbl, c_u32, c_vp]),
+    "ssq_ssq_stft_batch_diag_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl,
+                                            c_int, c_int, c_dbl, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ssq_stft_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "ssq_istft_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_i64, c_int,
                                     c_vp]),
@@ -155,6 +159,10 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         raise_status(load().ssq_ctx_set_stream(self._h, c_vp(cuda_stream_ptr or 0)), self._h)
+
+    def set_option(self, name: str, value: int):
+        """Kernel-selection switch (measurements / cross-checks; include/ssqcuda.h ssq_ctx_set_option)."""
+        raise_status(load().ssq_ctx_set_option(self._h, name.encode(), int(value)), self._h)
 
     def synchronize(self):
         raise_status(load().ssq_ctx_synchronize(self._h), self._h)

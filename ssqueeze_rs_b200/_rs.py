@@ -44,7 +44,11 @@ def _str(v, name):
 
 
 def hello_from_bin() -> str:
-    """lib.rs:16-19."""
+    """lib.rs:16-19 ("Hello from ssqueeze!"); `version()` identifies the CUDA library."""
+    return load().ssq_hello_from_bin().decode()
+
+
+def version() -> str:
     return load().ssq_version().decode()
 
 
@@ -73,7 +77,8 @@ def stft(x, n_fft, hop_length, window, padtype):
 def ssq_stft(x, window, n_fft=None, win_len=None, hop_len=1, fs=1.0, padtype="reflect", squeezing="sum",
              gamma=None, *, modulated=False, return_aux=False):
     """ssq_stft.rs:73-85.  Returns (Tx complex128 [n_freqs, n_frames], ssq_freqs).
-    `return_aux=True` appends a dict with Sx, dSx (complex128) and w (float64)."""
+    `return_aux=True` appends a dict with Sx, dSx (complex128), w (float64) and kb (int32: the destination
+    bin of every (source bin, frame), -1 where gated), written by the same kernel that produced Tx."""
     x = _f64_1d(x, "x")
     window = _f64_1d(window, "window")
     n = len(x)
@@ -82,6 +87,8 @@ def ssq_stft(x, window, n_fft=None, win_len=None, hop_len=1, fs=1.0, padtype="re
     hop = int(hop_len)
     if nf < 0 or wl < 0 or hop < 0:
         raise OverflowError("can't convert negative int to unsigned")
+    if nf == 0:  # pad = n_fft - 1 underflows (stft_utils.rs:20); also keeps the output shape below in step with the C side
+        raise _lib.PanicException("n_fft=0: attempt to subtract with overflow (stft_utils.rs:20)")
     if wl > nf:  # ssq_stft.rs:96-101 (before any shape arithmetic)
         raise ValueError(f"Window length {wl} cannot be greater than n_fft {nf}")
     ctx = default_context()
@@ -93,19 +100,20 @@ def ssq_stft(x, window, n_fft=None, win_len=None, hop_len=1, fs=1.0, padtype="re
     shape = (nf // 2 + 1, nfr.value)
     Tx = np.empty(shape, dtype=np.complex128)
     sf = np.empty(shape[0], dtype=np.float64)
-    Sx = dSx = w = None
+    Sx = dSx = w = kb = None
     if return_aux:
         Sx = np.empty(shape, dtype=np.complex128)
         dSx = np.empty(shape, dtype=np.complex128)
         w = np.empty(shape, dtype=np.float64)
+        kb = np.empty(shape, dtype=np.int32)
     flags = FLAG_MODULATED if modulated else 0
-    g = float(gamma) if gamma is not None else -1.0
+    g = float(gamma) if gamma is not None else float("nan")  # NaN = not given; negative values never gate
     st = lib.ssq_ssq_stft_f64(ctx.handle, _ptr(x), n, _ptr(window), len(window), nf, wl, hop, float(fs),
                               PAD.get(_str(padtype, "padtype"), 0), SQUEEZE.get(_str(squeezing, "squeezing"), 0),
-                              g, flags, _ptr(Tx), _ptr(sf), _ptr(Sx), _ptr(dSx), _ptr(w))
+                              g, flags, _ptr(Tx), _ptr(sf), _ptr(Sx), _ptr(dSx), _ptr(w), _ptr(kb))
     raise_status(st, ctx.handle)
     if return_aux:
-        return Tx, sf, dict(Sx=Sx, dSx=dSx, w=w)
+        return Tx, sf, dict(Sx=Sx, dSx=dSx, w=w, kb=kb)
     return Tx, sf
 
 
@@ -223,7 +231,7 @@ def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=3
     Tx = np.empty((ns, n), dtype=np.complex128)
     sf = np.empty(ns, dtype=np.float64)
     ctx = default_context()
-    g = float(gamma) if gamma is not None else -1.0
+    g = float(gamma) if gamma is not None else float("nan")
     st = load().ssq_ssq_cwt_f64(ctx.handle, _ptr(x), n, 1 if _str(wavelet, "wavelet") == "morlet" else 0, _ptr(sc),
                                 ns, dt, dist, PAD.get(_str(padtype, "padtype"), 0),
                                 SQUEEZE.get(_str(squeezing, "squeezing"), 0),

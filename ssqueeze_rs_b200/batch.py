@@ -33,12 +33,17 @@ class Engine:
 
     # ---- pointer level ---------------------------------------------------
     def ssq_stft_ptr(self, d_x, channels, n, window, n_fft, hop, fs, d_Tx, padtype="reflect", squeezing="sum",
-                     gamma=None, modulated=False, x_stride=0):
+                     gamma=None, modulated=False, x_stride=0, diag=None):
+        """diag: optional (d_Sx, d_dSx, d_w, d_kb) device addresses (0 = not wanted) -> the diagnostic twin."""
         w, wp = _wptr(window)
-        st = load().ssq_ssq_stft_batch_f32(self.ctx.handle, C.c_void_p(d_x), channels, n, x_stride or n, wp, len(w),
-                                           int(n_fft), int(hop), float(fs), PAD.get(padtype, 0),
-                                           SQUEEZE.get(squeezing, 0), -1.0 if gamma is None else float(gamma),
-                                           _lib.FLAG_MODULATED if modulated else 0, C.c_void_p(d_Tx))
+        args = (self.ctx.handle, C.c_void_p(d_x), channels, n, x_stride or n, wp, len(w),
+                int(n_fft), int(hop), float(fs), PAD.get(padtype, 0),
+                SQUEEZE.get(squeezing, 0), float("nan") if gamma is None else float(gamma),
+                _lib.FLAG_MODULATED if modulated else 0, C.c_void_p(d_Tx))
+        if diag is None:
+            st = load().ssq_ssq_stft_batch_f32(*args)
+        else:
+            st = load().ssq_ssq_stft_batch_diag_f32(*args, *[C.c_void_p(a or 0) for a in diag])
         raise_status(st, self.ctx.handle)
 
     def stft_ptr(self, d_x, channels, n, window, n_fft, hop, d_Sx, padtype="reflect", x_stride=0):
@@ -65,7 +70,7 @@ class Engine:
         w, wp = _wptr(window)
         st = load().ssq_ssq_stft_host_f32(self.ctx.handle, C.c_void_p(h_x), channels, n, wp, len(w), int(n_fft),
                                           int(hop), float(fs), PAD.get(padtype, 0), SQUEEZE.get(squeezing, 0),
-                                          -1.0 if gamma is None else float(gamma),
+                                          float("nan") if gamma is None else float(gamma),
                                           _lib.FLAG_MODULATED if modulated else 0, C.c_void_p(h_Tx))
         raise_status(st, self.ctx.handle)
 
@@ -77,8 +82,10 @@ class Engine:
         # stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1)
         self.ctx.set_stream(h if h else 1)
 
-    def ssq_stft(self, x, window, n_fft=512, hop_len=32, fs=1.0, out=None, **kw):
-        """x: float32 CUDA tensor [channels, n] -> complex64 [channels, n_freqs, n_frames]."""
+    def ssq_stft(self, x, window, n_fft=512, hop_len=32, fs=1.0, out=None, return_aux=False, **kw):
+        """x: float32 CUDA tensor [channels, n] -> complex64 [channels, n_freqs, n_frames].
+        return_aux: also a dict of device tensors Sx, dSx (complex64), w (float32), kb (int32) written by the same
+        kernel (diagnostic variant; parity tests)."""
         import torch
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
         ch, n = x.shape
@@ -86,8 +93,16 @@ class Engine:
         if out is None:
             out = torch.empty((ch, nfq, nfr), dtype=torch.complex64, device=x.device)
         self._bind_stream()
-        self.ssq_stft_ptr(x.data_ptr(), ch, n, window, n_fft, hop_len, fs, out.data_ptr(), x_stride=x.stride(0), **kw)
-        return out
+        if not return_aux:
+            self.ssq_stft_ptr(x.data_ptr(), ch, n, window, n_fft, hop_len, fs, out.data_ptr(), x_stride=x.stride(0), **kw)
+            return out
+        aux = dict(Sx=torch.empty_like(out), dSx=torch.empty_like(out),
+                   w=torch.empty((ch, nfq, nfr), dtype=torch.float32, device=x.device),
+                   kb=torch.empty((ch, nfq, nfr), dtype=torch.int32, device=x.device))
+        self.ssq_stft_ptr(x.data_ptr(), ch, n, window, n_fft, hop_len, fs, out.data_ptr(), x_stride=x.stride(0),
+                          diag=(aux["Sx"].data_ptr(), aux["dSx"].data_ptr(), aux["w"].data_ptr(), aux["kb"].data_ptr()),
+                          **kw)
+        return out, aux
 
     def stft(self, x, window, n_fft, hop_len, out=None, padtype="reflect"):
         import torch
@@ -166,7 +181,7 @@ class Engine:
                                           1 if wavelet == "morlet" else 0, C.c_void_p(sc.ctypes.data), len(sc), dt,
                                           1 if ssq_freqs == "linear" else 0, PAD.get(padtype, 0),
                                           SQUEEZE.get(squeezing, 0), 1 if maprange == "maximal" else 0,
-                                          -1.0 if gamma is None else float(gamma),
+                                          float("nan") if gamma is None else float(gamma),
                                           0 if flipud else _lib.FLAG_NO_FLIPUD, C.c_void_p(out.data_ptr()),
                                           C.c_void_p(sf.ctypes.data))
         raise_status(st, self.ctx.handle)
@@ -225,7 +240,7 @@ class SsqStftStream:
         h = C.c_void_p()
         st = load().ssq_stream_create(engine.ctx.handle, int(channels), int(n_total), int(max_chunk), wp, len(w),
                                       int(n_fft), int(hop_len), float(fs), PAD.get(padtype, 0),
-                                      SQUEEZE.get(squeezing, 0), -1.0 if gamma is None else float(gamma), C.byref(h))
+                                      SQUEEZE.get(squeezing, 0), float("nan") if gamma is None else float(gamma), C.byref(h))
         raise_status(st, engine.ctx.handle)
         self._h = h
 

@@ -85,9 +85,9 @@ static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int
     P.out = o;
     const int R = 1 << P.r, T = 1 << P.log2T;
     dim3 grid((unsigned)(L / ((int64_t)R * T)), (unsigned)rows);
-    if (P.r == 7 && P.log2T == 5 && (log2Ns == 0 || log2Ns >= 5) && !getenv("SSQ_NO_FFT128")) {
+    if (P.r == 7 && P.log2T == 5 && (log2Ns == 0 || log2Ns >= 5) && !ctx->opt.no_fft128) {
       // 64 columns per CTA (512 B runs) when the row is long enough; measured faster than 32
-      static const int tc_env = getenv("SSQ_FFT128_TC") ? atoi(getenv("SSQ_FFT128_TC")) : 64;
+      const int tc_env = ctx->opt.fft128_tc;
       const int tc = (tc_env == 32 || L < (int64_t)128 * 64 || (log2Ns > 0 && log2Ns < 6)) ? 32 : 64;
       dim3 g2((unsigned)(L / ((int64_t)128 * tc)), (unsigned)rows);
       const size_t sm = (size_t)tc * 129 * sizeof(float2);
@@ -157,8 +157,8 @@ static double cwt_denorm_constant(int wavelet) {
 // first radix-128 pass sees a single non-zero input per butterfly (t = 0): it is a broadcast,
 // its output at m is the spectrum at m >> 7, bit for bit.  When B <= L/128^2 the same holds for
 // the second pass.  Those passes are not run; the next pass reads the spectrum directly.
-static int cwt_skip_level(const CwtCall& c, const FftPlanHost& pl, int64_t si) {
-  if (pl.npass < 2 || pl.log2T != 5 || getenv("SSQ_NO_CWT_PRUNE")) return 0;
+static int cwt_skip_level(const ssq_ctx* ctx, const CwtCall& c, const FftPlanHost& pl, int64_t si) {
+  if (pl.npass < 2 || pl.log2T != 5 || ctx->opt.no_cwt_prune) return 0;
   const double scale = c.scales[si];
   if (!(scale > 0.0)) return 0;
   const double wmax = (c.wavelet == SSQ_WAVELET_MORLET) ? 14.5 : 4.5;
@@ -200,13 +200,28 @@ static ssq_status cwt_inverse_rows(ssq_ctx* ctx, const CwtCall& c, int log2L, co
   // rows are ordered (channel, scale, which): cut the range into runs of equal skip level
   int64_t r0 = g0;
   while (r0 < g1) {
-    const int lvl = cwt_skip_level(c, pl, (r0 / nd) % c.ns);
+    const int lvl = cwt_skip_level(ctx, c, pl, (r0 / nd) % c.ns);
     int64_t r1 = r0 + 1;
-    while (r1 < g1 && r1 - r0 < max_rows && cwt_skip_level(c, pl, (r1 / nd) % c.ns) == lvl) ++r1;
+    while (r1 < g1 && r1 - r0 < max_rows && cwt_skip_level(ctx, c, pl, (r1 / nd) % c.ns) == lvl) ++r1;
     B.row0 = r0;
     SSQ_TRY(fft_run(ctx, pl, B, (int)(r1 - r0), ws0, ws1, lvl));
     r0 = r1;
   }
+  return SSQ_OK;
+}
+
+// scales -> device fp32, cached by content (as stft_tables caches the window): a batched caller that repeats
+// the same scales pays neither a stream synchronisation nor a blocking copy per call
+static ssq_status cwt_upload_scales(ssq_ctx* ctx, const double* scales, int64_t ns) {
+  if (ctx->cwt_scales.p && (int64_t)ctx->cwt_scales_host.size() == ns &&
+      memcmp(ctx->cwt_scales_host.data(), scales, sizeof(double) * (size_t)ns) == 0)
+    return SSQ_OK;
+  std::vector<float> hs((size_t)ns);
+  for (int64_t i = 0; i < ns; ++i) hs[(size_t)i] = (float)scales[i];
+  SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, hs.size() * sizeof(float)));
+  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // queued kernels may still read the previous table
+  SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->cwt_scales_host.assign(scales, scales + ns);
   return SSQ_OK;
 }
 
@@ -225,11 +240,7 @@ static ssq_status cwt_prepare(ssq_ctx* ctx, const CwtCall& c, int* log2L, FftPla
   *pl = fft_plan(l2);
   SSQ_TRY(cwt_twiddles(ctx, l2, lo, hi, tw_s));
   // scales -> device fp32
-  std::vector<float> hs((size_t)c.ns);
-  for (int64_t i = 0; i < c.ns; ++i) hs[(size_t)i] = (float)c.scales[i];
-  SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, hs.size() * sizeof(float)));
-  SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice));
+  SSQ_TRY(cwt_upload_scales(ctx, c.scales, c.ns));
   *d_scales = (const float*)ctx->cwt_scales.p;
   // workspaces: x-hat [channels, L]; two ping-pong buffers of max_rows rows (multi-pass only)
   SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft0, (size_t)c.channels * L * sizeof(float2)));
@@ -239,7 +250,7 @@ static ssq_status cwt_prepare(ssq_ctx* ctx, const CwtCall& c, int* log2L, FftPla
     // multi-pass rows: keep the ping-pong workspaces of one batch inside L2 (126 MB) so that the
     // intermediate passes never reach HBM; the same addresses are rewritten by the next batch
     int64_t budget = (int64_t)2048 << 20;  // bytes per workspace (SSQ_CWT_WS_MB to experiment with L2-resident batches)
-    if (const char* e = getenv("SSQ_CWT_WS_MB")) budget = (int64_t)std::max(1, atoi(e)) << 20;
+    if (ctx->opt.cwt_ws_mb > 0) budget = ctx->opt.cwt_ws_mb << 20;
     *max_rows = std::max<int64_t>(1, std::min<int64_t>(*max_rows, budget / (L * 8)));
   }
   *ws0 = *ws1 = nullptr;
@@ -358,7 +369,7 @@ extern "C" ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int6
   ssq_cwt_grid(scales, ns, n, dt, maprange, freq_dist, f, &is_log, &f0, &inv_step);
   if (ssq_freqs) memcpy(ssq_freqs, f.data(), sizeof(double) * (size_t)ns);
   const double K = cwt_denorm_constant(c.wavelet);
-  const double g = (gamma >= 0.0) ? gamma : 10.0 * kEps64;
+  const double g = (gamma != gamma) ? 10.0 * kEps64 : gamma;  // NaN: not given; negative: never gates
   // per-channel W', dW' staging [ns, n] each
   const size_t stage = (size_t)ns * n * sizeof(float2);
   SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, stage));
@@ -463,11 +474,7 @@ extern "C" ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_
     const float2 *lo, *hi;
     int tw_s;
     SSQ_TRY(cwt_twiddles(ctx, l2, &lo, &hi, &tw_s));
-    std::vector<float> hs((size_t)ns);
-    for (int64_t i = 0; i < ns; ++i) hs[(size_t)i] = (float)scales[i];
-    SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, hs.size() * sizeof(float)));
-    SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SSQ_TRY(cwt_upload_scales(ctx, scales, ns));
     const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>(ns, ((int64_t)1 << 30) / (L * 8)));
     SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft0, (size_t)ns * L * sizeof(float2)));
     SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft1, (size_t)2 * max_rows * L * sizeof(float2)));
@@ -516,6 +523,7 @@ extern "C" ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_
   SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, hn.size() * sizeof(float)));
   SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, hn.data(), hn.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->cwt_scales_host.clear();  // the buffer no longer holds a scale table
   dim3 g((unsigned)((x_len + 255) / 256), (unsigned)channels);
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   icwt_kernel<<<g, 256, 0, ctx->stream>>>((const float2*)d_Wx, ns, n_cols, x_len, (const float*)ctx->cwt_scales.p,
@@ -564,6 +572,7 @@ extern "C" ssq_status ssq_issq_cwt_batch_f32(ssq_ctx* ctx, const float* d_Tx, in
   SSQ_TRY(devbuf_reserve(ctx, ctx->cwt_scales, ones.size() * sizeof(float)));
   SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->cwt_scales.p, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->cwt_scales_host.clear();
   dim3 g((unsigned)((n + 255) / 256), (unsigned)channels);
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   icwt_kernel<<<g, 256, 0, ctx->stream>>>((const float2*)d_Tx, ns, n, n, (const float*)ctx->cwt_scales.p,

@@ -15,7 +15,7 @@
 // unpad, de-normalisation constant), so Wx is written exactly once.
 #pragma once
 #include "ssq_common.cuh"
-#include "stft_fast.cuh"
+#include "fft_regs.cuh"
 
 struct FftPass {
   const float2* in;   // [rows, L] (unused by the first pass' functor loads)

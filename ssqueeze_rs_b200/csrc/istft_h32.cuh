@@ -18,7 +18,7 @@
 //     (at most two addends per element: exact and order-independent);
 //   * istft_finalize_kernel divides by the window norm and unpads.
 #pragma once
-#include "stft_h32.cuh"
+#include "fft_regs.cuh"
 
 // floor(p / hop) for 0 <= p < 2^23 without the ~20-instruction integer division: float estimate, then corrected
 // (the gather of the tile kernels divided twice per sample: 27 % of istft1024's instructions, ncu r1w)
@@ -43,156 +43,6 @@ struct Istft32Params {
   int hop;           // tile kernel: any hop >= 1 (the per-warp-run kernel needs hop == 32)
 };
 
-// 8-byte asynchronous global->shared copy.  A warp fetches 32 B row segments, so the four
-// sectors of a 128 B line are asked for by four consecutive quads of the same run: make L2
-// bring in the whole line on the first miss (.L2::128B) and keep it until the run has
-// passed (evict_last policy), otherwise DRAM reads 2.2x the input (profiles/README.md r1f).
-__device__ __forceinline__ uint64_t l2_evict_last_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int src_bytes, uint64_t pol) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint.L2::128B [%0], [%1], 8, %2, %3;" ::"r"(d), "l"(gsrc),
-               "r"(src_bytes), "l"(pol)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-__global__ void __launch_bounds__(H32_WARPS * 32, 2) istft512_h32_kernel(const Istft32Params P) {
-  constexpr int N = 512, AS = I32_AS;
-  extern __shared__ float2 smem[];
-  float2* tw2tab = smem;  // [8][9]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float2* xch = smem + 72 + warp * (N + 4 * AS);  // per warp: exchange [512] | tile [4][AS]
-  float2* tile = xch + N;
-  if (threadIdx.x < 64)
-    tw2tab[(threadIdx.x >> 3) * 9 + (threadIdx.x & 7)] = P.tw[((threadIdx.x >> 3) * (threadIdx.x & 7) * 8) & (N - 1)];
-
-  H32Lane L;
-  L.lane = lane;
-  L.j2 = lane + 32;  // inverse transform: no (k, N-k) pairing needed, keep the outputs lane-aligned
-  L.tw2 = tw2tab + (lane & 7) * 9;
-#pragma unroll
-  for (int t = 1; t < 8; ++t) {
-    L.tw3a[t - 1] = P.tw[(lane * t) & (N - 1)];
-    L.tw3b[t - 1] = P.tw[(L.j2 * t) & (N - 1)];
-  }
-  L.f1 = (lane >> 1) & 3;
-  L.rd1a = (lane >> 3) * 8 + ((((lane & 7) >> 1) ^ ((lane >> 4) & 3)) << 1) + (lane & 1);
-  L.rd1b = ((lane >> 3) + 4) * 8 + ((((lane & 7) >> 1) ^ (((lane >> 4) + 2) & 3)) << 1) + (lane & 1);
-  L.g2 = (lane >> 3) & 1;
-  L.wr2 = (lane >> 3) * 64 + (lane & 7);
-  L.lane_f = 0.f;
-  L.j2_f = 0.f;
-  L.l0 = (lane == 0);
-  const uint64_t pol = l2_evict_last_policy();
-  float war[16];  // window^a / N at n = lane + 32 j
-#pragma unroll
-  for (int j = 0; j < 16; ++j) war[j] = P.wa[lane + 32 * j];
-  __syncthreads();
-
-  const int fq = lane & 3, kr = lane >> 2;  // quad fetch: lane = (frame fq, row kr + 8 i)
-  for (int64_t run = (int64_t)blockIdx.x * H32_WARPS + warp; run < P.total_runs; run += (int64_t)gridDim.x * H32_WARPS) {
-    const int ch = (int)(run / P.runs_per_channel);
-    const int64_t f0 = (run % P.runs_per_channel) * P.run;
-    const int nfr = (int)min((int64_t)P.run, P.n_use - f0);
-    const float2* src = P.Sx + (size_t)ch * 257 * P.n_frames;
-    float* dst = P.xacc + (size_t)ch * P.L;
-    float out[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) out[j] = 0.f;
-
-    auto fetch_quad = [&](int q) {  // columns of frames f0+4q .. f0+4q+3 -> tile[fq][row]
-      const int64_t f = f0 + 4 * q + fq;
-      const bool fv = 4 * q + fq < nfr;
-      const float2* g = src + (size_t)kr * P.n_frames + (fv ? f : 0);
-      float2* t = tile + fq * AS + kr;
-      const size_t gstep = (size_t)8 * P.n_frames;
-#pragma unroll 8
-      for (int it = 0; it < 32; ++it) {
-        cp_async8(t + 8 * it, g, fv ? 8 : 0, pol);
-        g += gstep;
-      }
-      if (kr == 0) cp_async8(t + 256, g, fv ? 8 : 0, pol);  // row 256
-    };
-    auto emit = [&](int64_t block, float v) {  // padded positions 32*block + lane
-      const int64_t p = block * 32 + lane;
-      if (p < P.L) atomicAdd(dst + p, v);
-    };
-
-    const int nquads = (nfr + 3) >> 2;
-    fetch_quad(0);
-    for (int q = 0; q < nquads; ++q) {
-      cp_async_wait_all();
-      __syncwarp();
-#pragma unroll 1
-      for (int pr = 0; pr < 2; ++pr) {
-        const int fa = 4 * q + 2 * pr;
-        if (fa >= nfr) break;
-        const bool hasB = fa + 1 < nfr;
-        const float2* tA = tile + (2 * pr) * AS;
-        const float2* tB = tA + AS;  // zero-filled by the fetch when the frame does not exist
-        // ---- stage-1 inputs: conj(ZA + i ZB), Hermitian extension on the fly --------------------
-        float2 va[8], vb[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          if (t < 4) {
-            float2 a = tA[lane + 64 * t], b = tB[lane + 64 * t];
-            if (t == 0 && L.l0) { a.y = 0.f; b.y = 0.f; }  // DC: imaginary part ignored (irfft)
-            va[t] = make_float2(a.x - b.y, -(a.y + b.x));
-            a = tA[lane + 32 + 64 * t];
-            b = tB[lane + 32 + 64 * t];
-            vb[t] = make_float2(a.x - b.y, -(a.y + b.x));
-          } else {
-            // k = lane + 64 t > 256 (or == 256 for lane 0, t = 4): mirror k' = 512 - k
-            float2 a = tA[512 - 64 * t - lane], b = tB[512 - 64 * t - lane];
-            if (t == 4 && L.l0) { a.y = 0.f; b.y = 0.f; }  // Nyquist
-            va[t] = make_float2(a.x + b.y, a.y - b.x);
-            a = tA[480 - 64 * t - lane];
-            b = tB[480 - 64 * t - lane];
-            vb[t] = make_float2(a.x + b.y, a.y - b.x);
-          }
-        }
-        if (pr == 1 || fa + 2 >= nfr) {  // tile consumed: start fetching the next quad
-          __syncwarp();
-          if (q + 1 < nquads) fetch_quad(q + 1);
-        }
-        h32_fft512(L, xch, va, vb);  // va[m] = X[lane + 64 m], vb[m] = X[lane + 32 + 64 m]
-        __syncwarp();
-        // ---- overlap-add, frame A (real part) ---------------------------------------------------
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          out[2 * m] = fmaf(va[m].x, war[2 * m], out[2 * m]);
-          out[2 * m + 1] = fmaf(vb[m].x, war[2 * m + 1], out[2 * m + 1]);
-        }
-        emit(f0 + fa, out[0]);
-#pragma unroll
-        for (int j = 0; j < 15; ++j) out[j] = out[j + 1];
-        out[15] = 0.f;
-        if (hasB) {  // frame B = -Im
-#pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            out[2 * m] = fmaf(-va[m].y, war[2 * m], out[2 * m]);
-            out[2 * m + 1] = fmaf(-vb[m].y, war[2 * m + 1], out[2 * m + 1]);
-          }
-          emit(f0 + fa + 1, out[0]);
-#pragma unroll
-          for (int j = 0; j < 15; ++j) out[j] = out[j + 1];
-          out[15] = 0.f;
-        }
-      }
-    }
-    // tail of the run: blocks f0+nfr .. f0+nfr+14 hold partial sums shared with the next run
-#pragma unroll
-    for (int j = 0; j < 15; ++j) emit(f0 + nfr + j, out[j]);
-    __syncwarp();
-  }
-}
-
-
-// ------------------------------------------------------------------------------------
 // Tile variant (the one launched): the per-warp quad fetch above leaves every 128 B line
 // of Sx "open" for four quads of one warp; with 2368 warps that is ~78 MB of partially
 // consumed lines, L2 thrashes and DRAM reads 2.2x the input (ncu r1f).  Here a CTA owns

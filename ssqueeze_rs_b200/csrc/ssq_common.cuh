@@ -42,9 +42,17 @@ struct ssq_ctx {
   DevBuf cwt_tw;
   int64_t cwt_tw_n = -1;
   DevBuf cwt_scales;
+  std::vector<double> cwt_scales_host;  // content of cwt_scales (cache key)
   // pinned staging of the float64 entry points (two chunks: copy of chunk i+1 overlaps the conversion of chunk i)
   void* pin[2] = {nullptr, nullptr};
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  // kernel-selection switches (measurement and cross-checks only): seeded once from the
+  // environment (SSQ_<NAME>) by ssq_ctx_create, changed with ssq_ctx_set_option
+  struct Options {
+    int no_h32r = 0, h32r_nw = 0, no_r1024 = 0, no_r256 = 0, istft_nw = 8;
+    int no_fft128 = 0, fft128_tc = 64, no_cwt_prune = 0, no_cwt_fused = 0;
+    int64_t cwt_ws_mb = 0;
+  } opt;
 };
 
 static thread_local std::string g_tls_err;

@@ -4,8 +4,7 @@
 #include "ssq_common.cuh"
 #include "host_math.h"
 #include "stft_kernels.cuh"
-#include "stft_fast.cuh"
-#include "stft_h32.cuh"
+#include "fft_regs.cuh"
 #include "stft_h32r.cuh"
 #include "stft_r1024.cuh"
 #include "stft_r256.cuh"
@@ -25,8 +24,12 @@ static const double kEps64 = 2.2204460492503131e-16;
 // library / context
 // ===========================================================================
 extern "C" const char* ssq_version(void) {
-  return "ssqcuda 0.2 (B200 sm_100a; stft, ssq_stft, istft, issq_stft, cwt, cwt_simd, ssq_cwt, icwt, ssq_stft streaming)";
+  return "ssqcuda 0.3 (B200 sm_100a; stft, ssq_stft, istft, issq_stft, cwt, cwt_simd, ssq_cwt, icwt, issq_cwt, "
+         "ssq_stft streaming, ridge extraction)";
 }
+
+// lib.rs:16-19
+extern "C" const char* ssq_hello_from_bin(void) { return "Hello from ssqueeze!"; }
 
 extern "C" int ssq_device_count(void) {
   int n = 0;
@@ -70,7 +73,33 @@ extern "C" ssq_status ssq_ctx_create(int device, ssq_ctx** out) {
     return ssq_fail(nullptr, SSQ_ECUDA, "stream/event creation: %s", cudaGetErrorString(e));
   }
   c->stream = c->own_stream;
+  // switches: read from the environment once, here (never on the launch path)
+  static const char* const names[] = {"no_h32r", "h32r_nw", "no_r1024", "no_r256", "istft_nw", "no_fft128",
+                                      "fft128_tc", "no_cwt_prune", "no_cwt_fused", "cwt_ws_mb"};
+  for (const char* nm : names) {
+    std::string env = "SSQ_";
+    for (const char* q = nm; *q; ++q) env += (char)toupper((unsigned char)*q);
+    if (const char* v = getenv(env.c_str())) (void)ssq_ctx_set_option(c, nm, atoll(v));
+  }
   *out = c;
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_ctx_set_option(ssq_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return ssq_fail(ctx, SSQ_EINVAL, "ssq_ctx_set_option: NULL argument");
+  const std::string n(name);
+  ssq_ctx::Options& o = ctx->opt;
+  if (n == "no_h32r") o.no_h32r = value != 0;
+  else if (n == "h32r_nw") o.h32r_nw = (value == 4 || value == 8) ? (int)value : 0;
+  else if (n == "no_r1024") o.no_r1024 = value != 0;
+  else if (n == "no_r256") o.no_r256 = value != 0;
+  else if (n == "istft_nw") o.istft_nw = value == 4 ? 4 : 8;
+  else if (n == "no_fft128") o.no_fft128 = value != 0;
+  else if (n == "fft128_tc") o.fft128_tc = value == 32 ? 32 : 64;
+  else if (n == "no_cwt_prune") o.no_cwt_prune = value != 0;
+  else if (n == "no_cwt_fused") o.no_cwt_fused = value != 0;
+  else if (n == "cwt_ws_mb") o.cwt_ws_mb = value > 0 ? value : 0;
+  else return ssq_fail(ctx, SSQ_EINVAL, "ssq_ctx_set_option: unknown option '%s'", name);
   return SSQ_OK;
 }
 
@@ -298,6 +327,7 @@ struct StftCall {
   float2* aux_Sx;
   float2* aux_dSx;
   float* aux_w;
+  int* aux_kb = nullptr;
   // streaming (ssq_stream_*): compute frames [frame0, frame0 + n_frames_call) of a recording of n
   // samples, of which d_x holds [x_origin, ...)
   int64_t frame0 = 0;
@@ -340,9 +370,11 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   P.wpair = T.wpair;
   P.tw = T.tw;
   const double dw_f = 0.5 * c.fs / ((double)n_freqs - 1.0);  // ssq_stft.rs:50,273
-  const double gamma = (c.gamma >= 0.0) ? c.gamma : 10.0 * kEps64;  // NaN compares false -> default
+  // gamma: NaN = "not given" -> 10 eps (ssq_stft.rs:258-261); an explicit negative value never gates
+  // (|Sx| < gamma is always false, ssq_stft.rs:23)
+  const double gamma = (c.gamma != c.gamma) ? 10.0 * kEps64 : c.gamma;
   P.cphase = (float)(((double)n_freqs - 1.0) / (SSQ_PI * T.s_scale));
-  P.gate2 = (float)(4.0 * gamma * gamma);
+  P.gate2 = gamma < 0.0 ? -1.f : (float)std::min(4.0 * gamma * gamma, 3.0e38);
   P.tx_scale = (float)(0.5 * dw_f);
   P.leb_val = (float)(dw_f / (double)n_freqs);
   P.dw_f = (float)dw_f;
@@ -354,11 +386,12 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   P.aux_Sx = c.aux_Sx;
   P.aux_dSx = c.aux_dSx;
   P.aux_w = c.aux_w;
+  P.aux_kb = c.aux_kb;
 
-  const bool want_aux = c.aux_Sx || c.aux_dSx || c.aux_w;
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   bool done = false;
-  if (!want_aux) {
+  {  // diagnostic outputs (aux_*) do not change the kernel selection: the register kernels carry them as a
+     // compile-time variant of the same code
     ssq_status st = stft_h32r_launch(ctx, P, &done);
     if (st != SSQ_OK) return st;
     if (!done) {
@@ -367,14 +400,6 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
     }
     if (!done) {
       st = stft_r256_launch(ctx, P, &done);
-      if (st != SSQ_OK) return st;
-    }
-    if (!done && !streaming) {  // the older kernels do not take a frame offset
-      st = stft_h32_launch(ctx, P, &done);
-      if (st != SSQ_OK) return st;
-    }
-    if (!done && !streaming) {
-      st = stft_fast_launch(ctx, P, &done);
       if (st != SSQ_OK) return st;
     }
   }
@@ -398,10 +423,11 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
 // ---------------------------------------------------------------------------
 // batched device entry points
 // ---------------------------------------------------------------------------
-extern "C" ssq_status ssq_ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
-                                             int64_t x_stride, const double* window, int64_t win_n, int n_fft,
-                                             int hop, double fs, int padtype, int squeezing, double gamma,
-                                             unsigned flags, float* d_Tx) {
+extern "C" ssq_status ssq_ssq_stft_batch_diag_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                                  int64_t x_stride, const double* window, int64_t win_n, int n_fft,
+                                                  int hop, double fs, int padtype, int squeezing, double gamma,
+                                                  unsigned flags, float* d_Tx, float* d_Sx, float* d_dSx, float* d_w,
+                                                  int32_t* d_kb) {
   if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
   if (!d_x || !d_Tx || !window || win_n < 1) return ssq_fail(ctx, SSQ_EINVAL, "NULL/empty argument");
   if (n_fft <= 0) n_fft = (int)std::min<int64_t>(n, 512);  // ssq_stft.rs:92
@@ -422,10 +448,19 @@ extern "C" ssq_status ssq_ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int
   c.gamma = gamma;
   c.flags = flags;
   c.d_out = (float2*)d_Tx;
-  c.aux_Sx = nullptr;
-  c.aux_dSx = nullptr;
-  c.aux_w = nullptr;
+  c.aux_Sx = (float2*)d_Sx;
+  c.aux_dSx = (float2*)d_dSx;
+  c.aux_w = d_w;
+  c.aux_kb = d_kb;
   return run_stft_family(ctx, c);
+}
+
+extern "C" ssq_status ssq_ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                             int64_t x_stride, const double* window, int64_t win_n, int n_fft,
+                                             int hop, double fs, int padtype, int squeezing, double gamma,
+                                             unsigned flags, float* d_Tx) {
+  return ssq_ssq_stft_batch_diag_f32(ctx, d_x, channels, n, x_stride, window, win_n, n_fft, hop, fs, padtype, squeezing,
+                                     gamma, flags, d_Tx, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" ssq_status ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
@@ -480,7 +515,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
   SSQ_TRY(devbuf_reserve(ctx, ctx->ws_misc, (size_t)channels * L * sizeof(float)));
   SSQ_CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_misc.p, 0, (size_t)channels * L * sizeof(float), ctx->stream));
 
-  if (n_fft == 512 && !getenv("SSQ_NO_H32") && (hop == 32 || !getenv("SSQ_ISTFT_RUNS")) &&
+  if (n_fft == 512 && !ctx->opt.no_h32r &&
       (int64_t)31 * hop + 512 < ((int64_t)1 << 22)) {  // tile span inside the range of ssq_fast_div
     Istft32Params Q;
     memset(&Q, 0, sizeof(Q));
@@ -494,22 +529,9 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
     Q.xacc = (float*)ctx->ws_misc.p;
     Q.hop = hop;
     SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (getenv("SSQ_ISTFT_RUNS")) {  // per-warp runs with register overlap-add (kept for comparison)
-      int run = 32;
-      const int64_t warps = (int64_t)ctx->num_sms * 2 * H32_WARPS;
-      while (run > 4 && ((Q.n_use + run - 1) / run) * channels < warps) run >>= 1;
-      Q.run = run;
-      Q.runs_per_channel = (Q.n_use + run - 1) / run;
-      Q.total_runs = Q.runs_per_channel * channels;
-      const size_t smem = ((size_t)72 + (size_t)H32_WARPS * (512 + 4 * I32_AS)) * sizeof(float2);
-      const int grid = (int)std::min<int64_t>((Q.total_runs + H32_WARPS - 1) / H32_WARPS, (int64_t)ctx->num_sms * 2);
-      SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(istft512_h32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      istft512_h32_kernel<<<grid, H32_WARPS * 32, smem, ctx->stream>>>(Q);
-      SSQ_TRY(ssq_check_launch(ctx, "istft512_h32_kernel"));
-      ctx->last_kernel = "istft512_h32_kernel";
-    } else {
+    {
       // 8-warp CTAs / 32-frame tiles (SSQ_ISTFT_NW=4: 4 warps / 16 frames, 4 CTAs per SM -- measured 10.2 vs 9.5 ms)
-      static const int nw = getenv("SSQ_ISTFT_NW") ? atoi(getenv("SSQ_ISTFT_NW")) : 8;
+      const int nw = ctx->opt.istft_nw;
       const int F = nw == 8 ? 32 : 16, NWc = nw == 8 ? 8 : 4;
       Q.run = F;
       Q.runs_per_channel = (Q.n_use + F - 1) / F;
@@ -532,7 +554,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
     return SSQ_OK;
   }
 
-  if (n_fft == 256 && !getenv("SSQ_NO_R256")) {
+  if (n_fft == 256 && !ctx->opt.no_r256) {
     Istft32Params Q;
     memset(&Q, 0, sizeof(Q));
     Q.Sx = (const float2*)d_Sx;
@@ -566,7 +588,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
     }
   }
 
-  if (n_fft == 1024 && !getenv("SSQ_NO_R1024")) {
+  if (n_fft == 1024 && !ctx->opt.no_r1024) {
     Istft32Params Q;
     memset(&Q, 0, sizeof(Q));
     Q.Sx = (const float2*)d_Sx;
@@ -765,7 +787,7 @@ extern "C" ssq_status ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n, int
 extern "C" ssq_status ssq_ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n, const double* window,
                                        int64_t win_n, int n_fft, int win_len, int hop, double fs, int padtype,
                                        int squeezing, double gamma, unsigned flags, double* Tx, double* ssq_freqs,
-                                       double* Sx, double* dSx, double* w) {
+                                       double* Sx, double* dSx, double* w, int32_t* kb) {
   if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
   if (!x || !window || !Tx || win_n < 1) return ssq_fail(ctx, SSQ_EINVAL, "NULL/empty argument");
   SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -810,11 +832,19 @@ extern "C" ssq_status ssq_ssq_stft_f64(ssq_ctx* ctx, const double* x, int64_t n,
     SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux2, cnt * sizeof(float)));
     c.aux_w = (float*)ctx->ws_aux2.p;
   }
+  if (kb) {
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_misc, cnt * sizeof(int)));
+    c.aux_kb = (int*)ctx->ws_misc.p;
+  }
   SSQ_TRY(run_stft_family(ctx, c));
   SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_out.p, cnt * 2, Tx));
   if (Sx) SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_aux0.p, cnt * 2, Sx));
   if (dSx) SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_aux1.p, cnt * 2, dSx));
   if (w) SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_aux2.p, cnt, w));
+  if (kb) {
+    SSQ_CUDA_TRY(ctx, cudaMemcpyAsync(kb, ctx->ws_misc.p, cnt * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   if (ssq_freqs)  // ssq_stft.rs:42-54
     for (int64_t i = 0; i < n_freqs; ++i) ssq_freqs[i] = (double)i * 0.5 * fs / ((double)n_freqs - 1.0);
   return SSQ_OK;
@@ -1041,9 +1071,14 @@ static ssq_status stream_push(ssq_stream* s, const T* d_chunk, int64_t n_new, fl
   const int64_t have = s->received - s->origin;
   if (have + n_new > s->cap) return ssq_fail(ctx, SSQ_EINVAL, "internal: stream buffer overflow");
   float* buf = s->buf[s->cur];
-  if (n_new > 0) {
-    dim3 g((unsigned)((n_new + 31) / 32), (unsigned)((s->channels + 31) / 32)), b(32, 8);
-    deinterleave_kernel<T><<<g, b, 0, ctx->stream>>>(d_chunk, n_new, s->channels, scale, buf, s->cap, have);
+  // hop > n_fft: the buffer origin (start of the next frame) can lie beyond the samples received so far;
+  // the samples in between belong to no frame and are dropped here instead of being written before buf
+  const int64_t skip = std::min<int64_t>(n_new, std::max<int64_t>(0, -have));
+  if (n_new - skip > 0) {
+    const int64_t m = n_new - skip;
+    dim3 g((unsigned)((m + 31) / 32), (unsigned)((s->channels + 31) / 32)), b(32, 8);
+    deinterleave_kernel<T><<<g, b, 0, ctx->stream>>>(d_chunk + skip * s->channels, m, s->channels, scale, buf, s->cap,
+                                                     have + skip);
     SSQ_TRY(ssq_check_launch(ctx, "deinterleave_kernel"));
   }
   s->received += n_new;

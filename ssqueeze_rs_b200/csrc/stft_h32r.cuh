@@ -21,7 +21,7 @@
 // Accumulation order inside a bin is no longer ascending in k (rounding-level difference to
 // the reference); it is fixed by the schedule, so results stay run-to-run identical.
 #pragma once
-#include "stft_h32.cuh"
+#include "fft_regs.cuh"
 
 #ifndef H32R_PK
 #define H32R_PK(MODE) true  // packed fp32x2 arithmetic in the FFT, both modes (the stft mode spilled with it until the
@@ -40,9 +40,11 @@ struct H32RItem {
 // Pair (A, B) = (Z[k_a], Z[512 - k_a]) -> item of source bin |skf|.  sign(skf) < 0: roles swapped.
 // colB != nullptr (stft, hop 32): the FFT carried TWO frames, z = x_A w + i x_B w; the "V" half of the
 // split is then the second frame's spectrum and goes to its own column.
-template <int MODE, int SQZ>
+// DBG: also emit Sx, dSx, w and the destination bin of this source bin (ssq_dbg_emit) -- the parity tests run the
+// SAME kernel with one more store per item.
+template <int MODE, int SQZ, bool DBG = false>
 __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, float2* col, float2* colB, float skf,
-                                              float2 A, float2 B) {
+                                              float2 A, float2 B, size_t dbg_base = 0) {
   H32RItem it;
   const unsigned sgn = __float_as_uint(skf) & 0x80000000u;
   const float2 cd = add2<MODE == 0>(A, make_float2(B.x, -B.y));  // 2 Re Sx, +-2 Im Sx
@@ -67,6 +69,11 @@ __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, fl
   const float binf = fabsf(fmaf(-q0, P.cphase, skf));
   // nearest grid point, ties to the lower index, clamped; NaN converts to 0 -> bin 0 like the reference
   it.kb = min(max(__float2int_ru(binf - 0.5f), 0), 256);
+  if (DBG) {  // undo the role swap (Im Sx and Im V carry its sign) and apply the modulation sign
+    const float ms = (txs < 0.f) != (P.tx_scale < 0.f) ? -1.f : 1.f;
+    ssq_dbg_emit(P, dbg_base, (int)fabsf(skf), ms * c, ms * __uint_as_float(__float_as_uint(d0) ^ sgn), ms * a,
+                 ms * __uint_as_float(__float_as_uint(b0) ^ sgn), binf, den < P.gate2, it.kb);
+  }
   if (den < P.gate2) it.kb = -1;  // |Sx| < gamma (ssq_stft.rs:23): dropped
   if (SQZ == SSQ_SQUEEZE_LEBESGUE) {
     it.vre = P.leb_val;
@@ -109,12 +116,13 @@ __device__ __noinline__ void h32r_collision(float2* col, unsigned* T, int kb, fl
   }
 }
 
-template <int MODE, int SQZ>
+template <int MODE, int SQZ, bool DBG = false>
 // skf0: signed source bin of step 0; wrapd: increment applied instead of +64 after the step whose
 // source lies in [192, 256) (lanes >= 1: k_a jumps to the mirrored half, -448; lane 0: 192 -> 32).
 // txs: dw/2, negated on odd lanes when `modulated` (Sx[k] (-1)^k: every source bin of lane l has l's parity)
 __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L, float skf0, float wrapd, float txs,
-                                           float2* xch, float2* col, float2* colB, float2 (&va)[8], float2 (&vb)[8]) {
+                                           float2* xch, float2* col, float2* colB, float2 (&va)[8], float2 (&vb)[8],
+                                           size_t dbg_base = 0) {
   const int lane = L.lane;
   const bool l0 = L.l0;
   // tags alias the exchange buffer; one 32-bit word per destination bin: with byte tags four bins share a bank
@@ -137,7 +145,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
   float skf = skf0;
   {
     H32R_PAIR(0, A, B)
-    cur = h32r_item<MODE, SQZ>(P, txs, col, colB, skf, A, B);
+    cur = h32r_item<MODE, SQZ, DBG>(P, txs, col, colB, skf, A, B, dbg_base);
   }
   if (MODE == 0) {
     if (cur.kb >= 0) tagA[cur.kb] = (unsigned)lane;
@@ -151,7 +159,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
     if (r < 7) {  // next item's arithmetic overlaps this step's tag / accumulator latency
       skf += (skf >= 192.f) ? wrapd : 64.f;
       H32R_PAIR(r + 1, A, B)
-      nxt = h32r_item<MODE, SQZ>(P, txs, col, colB, skf, A, B);
+      nxt = h32r_item<MODE, SQZ, DBG>(P, txs, col, colB, skf, A, B, dbg_base);
     }
     if (MODE == 0) {
       unsigned* T = (r & 1) ? tagB : tagA;
@@ -179,7 +187,7 @@ __device__ __forceinline__ void h32r_frame(const StftParams& P, const H32Lane& L
 #undef H32R_PAIR
   // bin 256 = Z[256] of lane 0 (va[4], self-paired): last, outside the protocol
   if (l0) {
-    const H32RItem it = h32r_item<MODE, SQZ>(P, txs, col, colB, 256.f, va[4], va[4]);
+    const H32RItem it = h32r_item<MODE, SQZ, DBG>(P, txs, col, colB, 256.f, va[4], va[4], dbg_base);
     if (MODE == 0 && it.kb >= 0) smem_rmw_add(col + h32r_phys(it.kb), it.vre, it.vim);
   }
   __syncwarp();  // the tag area is the exchange buffer of the next frame
@@ -196,7 +204,7 @@ __device__ __noinline__ float h32r_edge_sample(const float* x, int64_t n, int64_
 // warps per SM, half the barrier domain).
 // SLIDE: hop == 32, the register sliding window (one new sample per lane and frame).  Otherwise any hop:
 // the 16 samples of every frame are (re)loaded, still a whole frame ahead of their use.
-template <int MODE, int SQZ, int NW, bool SLIDE>
+template <int MODE, int SQZ, int NW, bool SLIDE, bool DBG = false>
 __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(const StftParams P) {
   constexpr int N = 512, AS = H32R_AS, F = 4 * NW;
   // stft at hop 32: two frames per FFT (z = x_A w + i x_B w; frame B's samples are frame A's window
@@ -333,8 +341,9 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) ssq_stft512_h32r_kernel(cons
         }
       }
       if (active)
-        h32r_frame<MODE, SQZ>(P, L, skf0, wrapd, txs, xch, acc + (4 * warp + s) * AS,
-                              PAIR ? acc + (4 * warp + s + 1) * AS : nullptr, va, vb);
+        h32r_frame<MODE, SQZ, DBG>(P, L, skf0, wrapd, txs, xch, acc + (4 * warp + s) * AS,
+                                   PAIR ? acc + (4 * warp + s + 1) * AS : nullptr, va, vb,
+                                   DBG ? (size_t)tch * 257 * P.n_frames + tf0 + 4 * warp + s : 0);
     }
     if (!real) continue;
     __syncthreads();
@@ -380,7 +389,11 @@ static ssq_status stft_h32r_launch_nw(ssq_ctx* ctx, StftParams& P, bool* done) {
   const int grid = (int)std::min<int64_t>(P.total_tiles, (int64_t)ctx->num_sms * (16 / NW));
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
   void (*k)(const StftParams);
-  if (P.hop == 32)
+  const bool dbg = P.mode == 0 && (P.aux_Sx || P.aux_dSx || P.aux_w || P.aux_kb);
+  if (dbg)  // the same kernel with the diagnostic stores compiled in (parity tests)
+    k = P.hop == 32 ? (leb ? ssq_stft512_h32r_kernel<0, 1, NW, true, true> : ssq_stft512_h32r_kernel<0, 0, NW, true, true>)
+                    : (leb ? ssq_stft512_h32r_kernel<0, 1, NW, false, true> : ssq_stft512_h32r_kernel<0, 0, NW, false, true>);
+  else if (P.hop == 32)
     k = P.mode == 1 ? ssq_stft512_h32r_kernel<1, 0, NW, true>
         : leb       ? ssq_stft512_h32r_kernel<0, 1, NW, true>
                     : ssq_stft512_h32r_kernel<0, 0, NW, true>;
@@ -398,12 +411,10 @@ static ssq_status stft_h32r_launch_nw(ssq_ctx* ctx, StftParams& P, bool* done) {
 
 static ssq_status stft_h32r_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   *done = false;
-  if (P.n_fft != 512 || getenv("SSQ_NO_H32R")) return SSQ_OK;
-  if (P.hop != 32 && getenv("SSQ_H32R_HOP32_ONLY")) return SSQ_OK;
+  if (P.n_fft != 512 || ctx->opt.no_h32r) return SSQ_OK;
   // 4-warp CTAs (16-frame tiles, 128 B row segments) win for ssq_stft; the faster stft mode writes at
   // > 2.5 TB/s and needs the 256 B segments of the 8-warp shape at full scale (384 channels: 18.1 vs 26.5 ms)
-  static const int nw_force = getenv("SSQ_H32R_NW") ? atoi(getenv("SSQ_H32R_NW")) : 0;
-  const int nw_env = nw_force ? nw_force : (P.mode == 1 ? 8 : 4);
+  const int nw_env = ctx->opt.h32r_nw ? ctx->opt.h32r_nw : (P.mode == 1 ? 8 : 4);
   if (nw_env == 4) SSQ_TRY(stft_h32r_launch_nw<4>(ctx, P, done));
   else SSQ_TRY(stft_h32r_launch_nw<8>(ctx, P, done));
   return SSQ_OK;

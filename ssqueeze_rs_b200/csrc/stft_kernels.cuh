@@ -43,6 +43,7 @@ struct StftParams {
   float2* aux_Sx;       // optional, same shape
   float2* aux_dSx;      // optional
   float* aux_w;         // optional (Hz, +inf where gated)
+  int* aux_kb;          // optional: destination bin of every (source bin, frame), -1 where gated
   int64_t frame0;       // global index of local frame 0 (streaming: the call computes frames
                         // [frame0, frame0 + n_frames) of a recording of n samples, see ssq_stream_*)
   int64_t x_origin;     // global sample index of x[.][0] (0 unless streaming)
@@ -59,6 +60,18 @@ __device__ __forceinline__ int ssq_bin_from(float binf, int n_freqs) {
   return k;
 }
 
+
+// Diagnostic outputs of the ssq kernels (parity tests: a compile-time flag of the register kernels, never
+// on the timed path): per (source bin k, frame) Sx, dSx, w (Hz, +inf where gated) and the destination bin.
+// (c, d) = 2 Sx, (a, b) = 2 V as the kernel used them; base = (ch * n_freqs) * n_frames + local frame.
+__device__ __forceinline__ void ssq_dbg_emit(const StftParams& P, size_t base, int k, float c, float d, float a,
+                                             float b, float binf, bool gated, int kb) {
+  const size_t o = base + (size_t)k * P.n_frames;
+  if (P.aux_Sx) P.aux_Sx[o] = make_float2(0.5f * c, 0.5f * d);
+  if (P.aux_dSx) P.aux_dSx[o] = make_float2(a * P.dsx_scale, b * P.dsx_scale);
+  if (P.aux_w) P.aux_w[o] = gated ? __int_as_float(0x7f800000) : binf * P.dw_f;
+  if (P.aux_kb) P.aux_kb[o] = gated ? -1 : kb;
+}
 
 // Forward DFT of one frame held in shared memory by ONE warp.  A: input
 // (destroyed), B: scratch; returns the buffer holding the natural-order result.
@@ -188,10 +201,9 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
           const float den = c * c + d * d;
           const bool gated = den < P.gate2;  // |Sx| < gamma (ssq_stft.rs:23)
           const float binf = fabsf((float)k - (b * c - a * d) / den * P.cphase);
-          const size_t oidx = ((size_t)ch * P.n_freqs + k) * P.n_frames + frame;
-          if (P.aux_Sx) P.aux_Sx[oidx] = make_float2(0.5f * c, 0.5f * d);
-          if (P.aux_dSx) P.aux_dSx[oidx] = make_float2(a * P.dsx_scale, b * P.dsx_scale);
-          if (P.aux_w) P.aux_w[oidx] = gated ? __int_as_float(0x7f800000) : binf * P.dw_f;
+          if (P.mode == 0 && (P.aux_Sx || P.aux_dSx || P.aux_w || P.aux_kb))
+            ssq_dbg_emit(P, (size_t)ch * P.n_freqs * P.n_frames + frame, k, c, d, a, b, binf, gated,
+                         ssq_bin_from(binf, P.n_freqs));
           if (P.mode == 1) {
             col[k] = make_float2(0.5f * c, 0.5f * d);
           } else if (!gated) {

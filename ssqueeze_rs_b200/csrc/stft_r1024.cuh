@@ -85,9 +85,9 @@ struct R1KItem {
 };
 
 // A = Z[k], B = Z[1024 - k] -> item of source bin k (kf = (float)k).
-template <int MODE, int SQZ, int KMAX = 512>
+template <int MODE, int SQZ, int KMAX = 512, bool DBG = false>
 __device__ __forceinline__ R1KItem r1k_item(const StftParams& P, float txs, float2* col, float2* colB, int k,
-                                            float kf, float2 A, float2 B) {
+                                            float kf, float2 A, float2 B, size_t dbg_base = 0) {
   R1KItem it;
   const float c = A.x + B.x, d = A.y - B.y;  // 2 Sx
   if (MODE == 1) {
@@ -104,6 +104,10 @@ __device__ __forceinline__ R1KItem r1k_item(const StftParams& P, float txs, floa
   const float binf = fabsf(fmaf(-q, P.cphase, kf));
   // nearest grid point, ties to the lower index, clamped; NaN converts to 0 -> bin 0 like the reference
   it.kb = min(max(__float2int_ru(binf - 0.5f), 0), KMAX);
+  if (DBG) {  // diagnostic stores of the parity tests (with the modulation sign)
+    const float ms = (txs < 0.f) != (P.tx_scale < 0.f) ? -1.f : 1.f;
+    ssq_dbg_emit(P, dbg_base, k, ms * c, ms * d, ms * a, ms * b, binf, den < P.gate2, it.kb);
+  }
   if (den < P.gate2) it.kb = -1;  // |Sx| < gamma (ssq_stft.rs:23): dropped
   if (SQZ == SSQ_SQUEEZE_LEBESGUE) {
     it.vre = P.leb_val;
@@ -149,7 +153,7 @@ __device__ __noinline__ void r1k_collision(float2* col, unsigned* T, int kb, flo
 
 
 // NW warps per CTA, F frames per tile (F / NW per warp).
-template <int MODE, int SQZ, int NW, int F>
+template <int MODE, int SQZ, int NW, int F, bool DBG = false>
 __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftParams P) {
   constexpr int N = 1024, AS = R1K_AS, XS = R1K_XS, FPW = F / NW;
   constexpr bool PK = SSQ_PK_DEFAULT;
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
       if (fl >= nf) break;
       float2* col = acc + fl * AS;
       float2* colB = (MODE == 1 && fl + 1 < nf) ? col + AS : nullptr;
+      const size_t dbg_base = DBG ? (size_t)ch * 513 * P.n_frames + tf0 + fl : 0;
       float2 v[32];
       {
         const int64_t p0 = (P.frame0 + tf0 + fl) * (int64_t)P.hop + lane;  // padded position of t = 0
@@ -251,14 +256,14 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
         float2 B = make_float2(__shfl_sync(0xffffffffu, Bs.x, partner), __shfl_sync(0xffffffffu, Bs.y, partner));
         if (l0) B = v[R1K_REG((32 - m) & 31)];  // lane 0 pairs with itself: Z[1024 - 32 m]
         const int k = lane + 32 * m;
-        const R1KItem it = r1k_item<MODE, SQZ>(P, txs, col, colB, k, (float)k, A, B);
+        const R1KItem it = r1k_item<MODE, SQZ, 512, DBG>(P, txs, col, colB, k, (float)k, A, B, dbg_base);
         if (MODE == 0) {
           sval[k] = make_float2(it.vre, it.vim);
           skey[k] = it.kb;
         }
       }
       if (l0) {
-        const R1KItem it = r1k_item<MODE, SQZ>(P, txs, col, colB, 512, 512.f, v[R1K_REG(16)], v[R1K_REG(16)]);
+        const R1KItem it = r1k_item<MODE, SQZ, 512, DBG>(P, txs, col, colB, 512, 512.f, v[R1K_REG(16)], v[R1K_REG(16)], dbg_base);
         if (MODE == 0) {
           sval[512] = make_float2(it.vre, it.vim);
           skey[512] = it.kb;
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(NW * 32, 3) ssq_stft1024_kernel(const StftPara
 
 static ssq_status stft_r1024_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   *done = false;
-  if (P.n_fft != 1024 || getenv("SSQ_NO_R1024")) return SSQ_OK;
+  if (P.n_fft != 1024 || ctx->opt.no_r1024) return SSQ_OK;
   constexpr int NW = 4, F = 8;
   StftParams Q = P;
   Q.F = F;
@@ -352,7 +357,9 @@ static ssq_status stft_r1024_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   const size_t smem = ((size_t)F * R1K_AS + (size_t)NW * R1K_WS) * sizeof(float2);
   const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx->num_sms * 3);
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
+  const bool dbg = P.mode == 0 && (P.aux_Sx || P.aux_dSx || P.aux_w || P.aux_kb);
   void (*k)(const StftParams) = P.mode == 1 ? ssq_stft1024_kernel<1, 0, NW, F>
+                                : dbg       ? (leb ? ssq_stft1024_kernel<0, 1, NW, F, true> : ssq_stft1024_kernel<0, 0, NW, F, true>)
                                 : leb       ? ssq_stft1024_kernel<0, 1, NW, F>
                                             : ssq_stft1024_kernel<0, 0, NW, F>;
   SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

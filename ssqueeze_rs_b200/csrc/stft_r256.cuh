@@ -55,7 +55,7 @@ __device__ __noinline__ void r256_collision(float2* col, unsigned short* T, int 
 }
 
 // NW warps per CTA, F frames per tile (groups of four per warp).
-template <int MODE, int SQZ, int NW, int F>
+template <int MODE, int SQZ, int NW, int F, bool DBG = false>
 __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel(const StftParams P) {
   constexpr int N = 256, AS = R256_AS, XS = R1K_XS, SS = R256_SS, GPW = F / (4 * NW);
   constexpr bool PK = SSQ_PK_DEFAULT;
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
       const bool live = fl < nf;  // frames past the end compute on zeros; their columns are never stored
       float2* col = acc + fl * AS + 8 * (fl & 1);
       float2* colB = (MODE == 1) ? col + 4 * AS : nullptr;  // (a column past nf is written but never stored)
+      const size_t dbg_base = DBG ? (size_t)ch * 129 * P.n_frames + tf0 + fl : 0;
       float2 v[32];
       {
         const int64_t p0 = (P.frame0 + tf0 + fl) * (int64_t)P.hop + c;  // padded position of t = 0
@@ -181,7 +182,8 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
           float2 B = make_float2(__shfl_sync(0xffffffffu, Bs.x, partner), __shfl_sync(0xffffffffu, Bs.y, partner));
           if (c0) B = j ? v[8 * (4 - j) + 7 - m] : v[(8 - m) & 7];  // c = 0 pairs with itself
           const int k = c + 8 * j + 32 * m;
-          const R1KItem it = r1k_item<MODE, SQZ, 128>(P, txs, col, colB, k, (float)k, A, B);
+          const R1KItem it = (DBG && live) ? r1k_item<MODE, SQZ, 128, true>(P, txs, col, colB, k, (float)k, A, B, dbg_base)
+                                           : r1k_item<MODE, SQZ, 128>(P, txs, col, colB, k, (float)k, A, B);
           if (MODE == 0) {
             sval[k] = make_float2(it.vre, it.vim);
             skey[k] = it.kb;
@@ -189,7 +191,8 @@ __global__ void __launch_bounds__(NW * 32, MODE == 0 ? 4 : 3) ssq_stft256_kernel
         }
       }
       if (c0) {
-        const R1KItem it = r1k_item<MODE, SQZ, 128>(P, txs, col, colB, 128, 128.f, v[4], v[4]);
+        const R1KItem it = (DBG && live) ? r1k_item<MODE, SQZ, 128, true>(P, txs, col, colB, 128, 128.f, v[4], v[4], dbg_base)
+                                         : r1k_item<MODE, SQZ, 128>(P, txs, col, colB, 128, 128.f, v[4], v[4]);
         if (MODE == 0) {
           sval[128] = make_float2(it.vre, it.vim);
           skey[128] = it.kb;
@@ -283,6 +286,8 @@ static ssq_status stft_r256_launch_f(ssq_ctx* ctx, StftParams& P, bool* done) {
   const bool leb = P.squeezing == SSQ_SQUEEZE_LEBESGUE;
   void (*k)(const StftParams);
   if constexpr (F == 32) k = ssq_stft256_kernel<1, 0, NW, F>;
+  else if (P.aux_Sx || P.aux_dSx || P.aux_w || P.aux_kb)
+    k = leb ? ssq_stft256_kernel<0, 1, NW, F, true> : ssq_stft256_kernel<0, 0, NW, F, true>;
   else k = leb ? ssq_stft256_kernel<0, 1, NW, F> : ssq_stft256_kernel<0, 0, NW, F>;
   SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<grid, NW * 32, smem, ctx->stream>>>(Q);
@@ -295,7 +300,7 @@ static ssq_status stft_r256_launch_f(ssq_ctx* ctx, StftParams& P, bool* done) {
 
 static ssq_status stft_r256_launch(ssq_ctx* ctx, StftParams& P, bool* done) {
   *done = false;
-  if (P.n_fft != 256 || getenv("SSQ_NO_R256")) return SSQ_OK;
+  if (P.n_fft != 256 || ctx->opt.no_r256) return SSQ_OK;
   // ssq: 16-frame tiles (one group of four frames per warp); stft: 32-frame tiles, two groups per FFT
   return P.mode == 1 ? stft_r256_launch_f<4, 32>(ctx, P, done) : stft_r256_launch_f<4, 16>(ctx, P, done);
 }

@@ -28,7 +28,8 @@ def test_header_symbols_exported(built_lib):
 
 def test_version_and_shapes(built_lib):
     from ssqueeze_rs_b200 import _rs
-    assert "ssqcuda" in _rs.hello_from_bin()
+    assert _rs.hello_from_bin() == "Hello from ssqueeze!"  # lib.rs:16-19
+    assert "ssqcuda" in _rs.version()
     a, b = ctypes.c_int64(), ctypes.c_int64()
     assert built_lib.ssq_stft_shape(1000, 256, 64, ctypes.byref(a), ctypes.byref(b)) == 0
     assert (a.value, b.value) == (129, 16)  # tests/stft_test.py expected shape
@@ -61,6 +62,9 @@ def test_argument_validation_without_gpu(built_lib):
         _rs.ssq_stft(x, np.ones(32), n_fft=16)  # ssq_stft.rs:96-101, raised before any device work
     with pytest.raises(ValueError):
         _rs.cwt(x, t=np.array([0.0]))  # cwt.rs:68-70
+    from ssqueeze_rs_b200 import PanicException
+    with pytest.raises(PanicException):
+        _rs.ssq_stft(x, np.ones(0), n_fft=0, win_len=0)  # n_fft - 1 underflows (stft_utils.rs:20); no buffer is sized from it
 
 
 def test_no_cpu_fallback(built_lib):

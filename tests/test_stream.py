@@ -56,3 +56,12 @@ def test_stream_other_kernels_and_hops():
     assert "1024" in _run(20000, 3, [4100, 999], 1024, 256, "i16")
     _run(6000, 2, [1700], 512, 300, "i16")              # hop > n_fft/2: end-reflection reaches before the frame start
     assert "generic" in _run(4000, 2, [1111], 128, 1, "f32")
+
+
+def test_stream_hop_larger_than_n_fft_small_chunks():
+    """hop > n_fft with chunks smaller than the hop: the start of the next frame lies beyond the samples received so
+    far, the samples in between belong to no frame (they must be dropped, not written before the carry-over buffer)."""
+    _run(30000, 3, [300], 512, 1000, "f32")
+    _run(30000, 2, [300, 77, 1500], 512, 512 + 17, "i16")
+    assert "256" in _run(9000, 4, [100], 256, 256 + 17, "f32")
+    _run(5000, 2, [64], 128, 700, "f32")                # generic kernel
