@@ -153,11 +153,14 @@ ssq_status ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet,
                        unsigned flags, double* Wx, double* dWx);
 
 /* replaces the body of `ssq_cwt` (ssq_cwt.rs:261-493).
- * Tx complex128 [ns, n]; ssq_freqs float64 [ns] (not flipped, :482). */
+ * Tx complex128 [ns, n]; ssq_freqs float64 [ns] (not flipped, :482).  gamma: NaN = not given (10*EPS64).
+ * Optional diagnostics (may be NULL), written by the reassignment itself: w float64 [ns, n] (the phase transform,
+ * +inf where gated), kb int32 [ns, n]: the Tx row every (scale, column) was added to, -1 where nothing was added
+ * (gated, w not finite, bin outside the grid: ssq_cwt.rs:165-190). */
 ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet,
                            const double* scales, int64_t ns, double dt, int freq_dist,
                            int padtype, int squeezing, int maprange, double gamma,
-                           unsigned flags, double* Tx, double* ssq_freqs);
+                           unsigned flags, double* Tx, double* ssq_freqs, double* w, int32_t* kb);
 
 /* `icwt`: cwt.rs:548-718, a #[pyfunction] the reference module never registers.
  * One-integral branch (:590-627, the default): x[j] = (2/adm) dj sum_i Re Wx[i,j] norm_i + x_mean.
@@ -227,6 +230,13 @@ ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channel
                                  int64_t ns, double dt, int freq_dist, int padtype,
                                  int squeezing, int maprange, double gamma, unsigned flags,
                                  float* d_Tx, double* ssq_freqs);
+
+/* diagnostic twin: d_w fp32, d_kb int32, each [channels, ns, n] (may be NULL) */
+ssq_status ssq_ssq_cwt_batch_diag_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                      int64_t x_stride, int wavelet, const double* scales,
+                                      int64_t ns, double dt, int freq_dist, int padtype,
+                                      int squeezing, int maprange, double gamma, unsigned flags,
+                                      float* d_Tx, double* ssq_freqs, float* d_w, int32_t* d_kb);
 
 /* d_Wx complex64 [channels, ns, n_cols] -> d_x fp32 [channels, x_len] */
 ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_t channels, int64_t ns, int64_t n_cols,

@@ -201,7 +201,7 @@ def emulate_fp32_kernel(x, window, n_fft, hop, fs, padtype="reflect", gamma=None
 # e_W[i] = eps32 (C_CWT rms_n|W_i| + C_FFT ||x_pad||_2 ||psi-hat_i||_2 / L), same for dW with psi-hat xi / dt.
 # w = |Im(dW / W)| / 2 pi moves by (e_D + |dW/W| e_W) / (2 pi |W|); the bin coordinate is (w - f0) / step or
 # (log2 w - f0) / step, rounded half away from zero; bins outside the grid are dropped.
-C_CWT = 64.0
+C_CWT = 128.0
 
 
 def cwt_bin_tolerance(aux_o, x, wavelet, dt, padtype, ssq_freqs):

@@ -57,7 +57,9 @@ SIGNATURES = {
     "ssq_issq_stft_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_vp]),
     "ssq_cwt_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_dbl, c_int, c_u32, c_vp, c_vp]),
     "ssq_ssq_cwt_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_dbl, c_int, c_int, c_int, c_int,
-                                c_dbl, c_u32, c_vp, c_vp]),
+                                c_dbl, c_u32, c_vp, c_vp, c_vp, c_vp]),
+    "ssq_ssq_cwt_batch_diag_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_dbl, c_int, c_int,
+                                           c_int, c_int, c_dbl, c_u32, c_vp, c_vp, c_vp, c_vp]),
     "ssq_icwt_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_i64, c_dbl, c_u32, c_vp]),
     "ssq_cwt_admissibility": (c_int, [c_int, c_vp]),
     "ssq_issq_cwt_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),

@@ -217,9 +217,12 @@ def cwt_simd(x, wavelet="gmw", scales=None, fs=None, t=None, nv=32, l1_norm=True
 
 
 def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=32, padtype="reflect",
-            squeezing="sum", maprange="peak", difftype="trig", gamma=None, vectorized=True, flipud=True):
+            squeezing="sum", maprange="peak", difftype="trig", gamma=None, vectorized=True, flipud=True, *,
+            return_aux=False):
     """ssq_cwt.rs:245-277.  Returns (Tx complex128 [n_scales, N], ssq_freqs).
-    `difftype` / `vectorized` are ignored as in the reference (:296-297)."""
+    `difftype` / `vectorized` are ignored as in the reference (:296-297).
+    `return_aux=True` (not in the reference) appends a dict with w (float64, the phase transform) and kb (int32: the
+    Tx row every (scale, column) was added to, -1: nothing added), written by the reassignment itself."""
     x = _f64_1d(x, "x")
     n = len(x)
     dt = _dt(fs, t)
@@ -230,14 +233,18 @@ def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=3
     dist = 1 if (ssq_freqs is not None and _str(ssq_freqs, "ssq_freqs") == "linear") else 0
     Tx = np.empty((ns, n), dtype=np.complex128)
     sf = np.empty(ns, dtype=np.float64)
+    w = np.empty((ns, n), dtype=np.float64) if return_aux else None
+    kb = np.empty((ns, n), dtype=np.int32) if return_aux else None
     ctx = default_context()
     g = float(gamma) if gamma is not None else float("nan")
     st = load().ssq_ssq_cwt_f64(ctx.handle, _ptr(x), n, 1 if _str(wavelet, "wavelet") == "morlet" else 0, _ptr(sc),
                                 ns, dt, dist, PAD.get(_str(padtype, "padtype"), 0),
                                 SQUEEZE.get(_str(squeezing, "squeezing"), 0),
                                 1 if _str(maprange, "maprange") == "maximal" else 0, g,
-                                0 if flipud else FLAG_NO_FLIPUD, _ptr(Tx), _ptr(sf))
+                                0 if flipud else FLAG_NO_FLIPUD, _ptr(Tx), _ptr(sf), _ptr(w), _ptr(kb))
     raise_status(st, ctx.handle)
+    if return_aux:
+        return Tx, sf, dict(w=w, kb=kb, scales=sc)
     return Tx, sf
 
 

@@ -169,21 +169,29 @@ class Engine:
         return (Wx, dWx) if derivative else Wx
 
     def ssq_cwt(self, x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=32, padtype="reflect",
-                squeezing="sum", maprange="peak", gamma=None, flipud=True, out=None, return_freqs=False):
-        """x: float32 CUDA [channels, n] -> Tx complex64 [channels, ns, n]."""
+                squeezing="sum", maprange="peak", gamma=None, flipud=True, out=None, return_freqs=False,
+                return_aux=False):
+        """x: float32 CUDA [channels, n] -> Tx complex64 [channels, ns, n].
+        return_aux: (Tx, ssq_freqs, dict(w float32, kb int32, scales)) -- diagnostics written by the reassignment."""
         import torch
         ch, n, sc, dt = self._cwt_args(x, scales, fs, t, nv)
         if out is None:
             out = torch.empty((ch, len(sc), n), dtype=torch.complex64, device=x.device)
         sf = np.empty(len(sc), dtype=np.float64)
         self._bind_stream()
-        st = load().ssq_ssq_cwt_batch_f32(self.ctx.handle, C.c_void_p(x.data_ptr()), ch, n, x.stride(0),
-                                          1 if wavelet == "morlet" else 0, C.c_void_p(sc.ctypes.data), len(sc), dt,
-                                          1 if ssq_freqs == "linear" else 0, PAD.get(padtype, 0),
-                                          SQUEEZE.get(squeezing, 0), 1 if maprange == "maximal" else 0,
-                                          float("nan") if gamma is None else float(gamma),
-                                          0 if flipud else _lib.FLAG_NO_FLIPUD, C.c_void_p(out.data_ptr()),
-                                          C.c_void_p(sf.ctypes.data))
+        args = (self.ctx.handle, C.c_void_p(x.data_ptr()), ch, n, x.stride(0),
+                1 if wavelet == "morlet" else 0, C.c_void_p(sc.ctypes.data), len(sc), dt,
+                1 if ssq_freqs == "linear" else 0, PAD.get(padtype, 0),
+                SQUEEZE.get(squeezing, 0), 1 if maprange == "maximal" else 0,
+                float("nan") if gamma is None else float(gamma),
+                0 if flipud else _lib.FLAG_NO_FLIPUD, C.c_void_p(out.data_ptr()), C.c_void_p(sf.ctypes.data))
+        if return_aux:
+            w = torch.empty((ch, len(sc), n), dtype=torch.float32, device=x.device)
+            kb = torch.empty((ch, len(sc), n), dtype=torch.int32, device=x.device)
+            st = load().ssq_ssq_cwt_batch_diag_f32(*args, C.c_void_p(w.data_ptr()), C.c_void_p(kb.data_ptr()))
+            raise_status(st, self.ctx.handle)
+            return out, sf, dict(w=w, kb=kb, scales=sc)
+        st = load().ssq_ssq_cwt_batch_f32(*args)
         raise_status(st, self.ctx.handle)
         return (out, sf) if return_freqs else out
 

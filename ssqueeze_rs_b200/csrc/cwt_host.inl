@@ -16,20 +16,39 @@ static FftPlanHost fft_plan(int log2L) {
     p.log2T = 0;
     return p;
   }
-  // 7-bit passes first (fft128_pass_kernel: register butterflies), the remainder in one or two
-  // generic passes of >= 4 bits at the end (their Ns is then >= 128 >= T)
-  int n7 = log2L / 7, rem = log2L - 7 * n7;
+  // 7-bit register passes (fft128_pass_kernel) first AND last, the remaining bits in one or two generic passes in
+  // the middle: the first pass generates x-hat psi-hat on the fly and can be skipped for band-limited rows
+  // (cwt_skip_level), the last pass carries the fused ssq_cwt epilogue -- both want the fast kernel.
   p.npass = 0;
-  if (rem == 0) {
-    for (int i = 0; i < n7; ++i) p.r[p.npass++] = 7;
-  } else if (rem >= 4) {
-    for (int i = 0; i < n7; ++i) p.r[p.npass++] = 7;
-    p.r[p.npass++] = rem;
-  } else {
-    for (int i = 0; i < n7 - 1; ++i) p.r[p.npass++] = 7;
-    const int two = 7 + rem;  // 8..10 bits in two generic passes
-    p.r[p.npass++] = (two + 1) / 2;
-    p.r[p.npass++] = two / 2;
+  if (log2L >= 18) {
+    const int rem = log2L - 14;  // 4 .. 13 bits between the two 7-bit passes
+    p.r[p.npass++] = 7;
+    if (rem == 7) {
+      p.r[p.npass++] = 7;
+    } else if (rem <= 7) {
+      p.r[p.npass++] = rem;
+    } else if (rem >= 11) {
+      p.r[p.npass++] = 7;
+      p.r[p.npass++] = rem - 7;
+    } else {  // 8 .. 10
+      p.r[p.npass++] = (rem + 1) / 2;
+      p.r[p.npass++] = rem / 2;
+    }
+    p.r[p.npass++] = 7;
+  } else if (log2L == 14) {
+    p.r[p.npass++] = 7;
+    p.r[p.npass++] = 7;
+  } else {  // 13, 15 .. 17: 7-bit passes first, the remainder in one or two generic passes of >= 4 bits
+    const int n7 = log2L / 7, rem = log2L - 7 * n7;
+    if (rem >= 4) {
+      for (int i = 0; i < n7; ++i) p.r[p.npass++] = 7;
+      p.r[p.npass++] = rem;
+    } else {
+      for (int i = 0; i < n7 - 1; ++i) p.r[p.npass++] = 7;
+      const int two = 7 + rem;  // 8 .. 10 bits in two generic passes
+      p.r[p.npass++] = (two + 1) / 2;
+      p.r[p.npass++] = two / 2;
+    }
   }
   p.log2T = 5;
   return p;
@@ -85,7 +104,15 @@ static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int
     P.out = o;
     const int R = 1 << P.r, T = 1 << P.log2T;
     dim3 grid((unsigned)(L / ((int64_t)R * T)), (unsigned)rows);
-    if (P.r == 7 && P.log2T == 5 && (log2Ns == 0 || log2Ns >= 5) && !ctx->opt.no_fft128) {
+    if (last && base.store_mode == 2) {
+      // fused ssq_cwt epilogue: lane pairs carry the W and dW rows of one scale, 32 columns per CTA of 512 threads
+      // (cwt_fused_ok guarantees r == 7, log2Ns >= 6 and an even number of rows starting at an even row)
+      dim3 g2((unsigned)(L / ((int64_t)128 * 32)), (unsigned)(rows / 2));
+      const size_t sm = (size_t)64 * 129 * sizeof(float2);
+      SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(fft128_pass_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      fft128_pass_kernel<64, true><<<g2, 512, sm, ctx->stream>>>(P);
+      SSQ_TRY(ssq_check_launch(ctx, "fft128_pass_kernel<fused ssq_cwt>"));
+    } else if (P.r == 7 && P.log2T == 5 && (log2Ns == 0 || log2Ns >= 5) && !ctx->opt.no_fft128) {
       // 64 columns per CTA (512 B runs) when the row is long enough; measured faster than 32
       const int tc_env = ctx->opt.fft128_tc;
       const int tc = (tc_env == 32 || L < (int64_t)128 * 64 || (log2Ns > 0 && log2Ns < 6)) ? 32 : 64;
@@ -164,9 +191,13 @@ static int cwt_skip_level(const ssq_ctx* ctx, const CwtCall& c, const FftPlanHos
   const double wmax = (c.wavelet == SSQ_WAVELET_MORLET) ? 14.5 : 4.5;
   const double L = (double)((int64_t)1 << pl.log2L);
   const double B = wmax * L / (2.0 * SSQ_PI * scale) * (1.0 + 1e-4) + 2.0;
+  // the first pass (and then the second) is a broadcast when the band ends below L / 2^r0 (L / 2^(r0 + r1)); at
+  // least one pass must remain
+  // (any radices: with only t = 0 non-zero a Stockham pass of radix 2^r copies its input at j to the outputs
+  // Ns (q 2^r + t') + k, j = Ns q + k -- the spectrum at m >> (bits so far))
   int lvl = 0;
-  if (pl.r[0] == 7 && B <= L / 128.0) lvl = 1;
-  if (lvl == 1 && pl.npass >= 3 && pl.r[1] == 7 && B <= L / 16384.0) lvl = 2;
+  if (B <= L / (double)((int64_t)1 << pl.r[0])) lvl = 1;
+  if (lvl == 1 && pl.npass >= 3 && B <= L / (double)((int64_t)1 << (pl.r[0] + pl.r[1]))) lvl = 2;
   return lvl;
 }
 
@@ -175,7 +206,7 @@ static ssq_status cwt_inverse_rows(ssq_ctx* ctx, const CwtCall& c, int log2L, co
                                    const float2* lo, const float2* hi, int tw_s, const float2* xhat,
                                    const float* d_scales, int nd, float2* outW, float2* outD, int64_t out_cols,
                                    int64_t n1, float out_scale, int64_t g0, int64_t g1, float2* ws0, float2* ws1,
-                                   int64_t max_rows) {
+                                   int64_t max_rows, const SsqCwtParams* fused = nullptr) {
   FftPass B;
   memset(&B, 0, sizeof(B));
   B.sign = +1;
@@ -196,6 +227,11 @@ static ssq_status cwt_inverse_rows(ssq_ctx* ctx, const CwtCall& c, int log2L, co
   B.n1 = n1;
   B.out_scale = out_scale;
   B.l2_norm = (c.flags & SSQ_FLAG_L2_NORM) ? 1 : 0;
+  if (fused) {  // last pass = fused ssq_cwt epilogue: row pairs (W, dW) must stay together
+    B.store_mode = 2;
+    B.E = *fused;
+    max_rows = std::max<int64_t>(2, max_rows & ~(int64_t)1);
+  }
   if (g1 > (int64_t)0x7fffffff) return ssq_fail(ctx, SSQ_EUNSUPPORTED, "cwt: more than 2^31 rows in one call");
   // rows are ordered (channel, scale, which): cut the range into runs of equal skip level
   int64_t r0 = g0;
@@ -337,10 +373,18 @@ static void ssq_cwt_grid(const double* scales, int64_t ns, int64_t n, double dt,
   }
 }
 
-extern "C" ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
-                                            int64_t x_stride, int wavelet, const double* scales, int64_t ns,
-                                            double dt, int freq_dist, int padtype, int squeezing, int maprange,
-                                            double gamma, unsigned flags, float* d_Tx, double* ssq_freqs) {
+// The last pass can carry the fused epilogue when it is a 7-bit register pass whose outputs of adjacent columns are
+// adjacent (Ns >= 32) and the row fits 32-bit column arithmetic.
+static bool cwt_fused_ok(const ssq_ctx* ctx, const FftPlanHost& pl, int64_t n) {
+  if (ctx->opt.no_cwt_fused || ctx->opt.no_fft128 || pl.npass < 2 || pl.log2T != 5) return false;
+  return pl.r[pl.npass - 1] == 7 && pl.log2L - 7 >= 5 && pl.log2L >= 12 && n < ((int64_t)1 << 30);
+}
+
+extern "C" ssq_status ssq_ssq_cwt_batch_diag_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                                 int64_t x_stride, int wavelet, const double* scales, int64_t ns,
+                                                 double dt, int freq_dist, int padtype, int squeezing, int maprange,
+                                                 double gamma, unsigned flags, float* d_Tx, double* ssq_freqs,
+                                                 float* d_w, int32_t* d_kb) {
   if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
   if (!d_x || !scales || !d_Tx) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
   CwtCall c;
@@ -370,34 +414,54 @@ extern "C" ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int6
   if (ssq_freqs) memcpy(ssq_freqs, f.data(), sizeof(double) * (size_t)ns);
   const double K = cwt_denorm_constant(c.wavelet);
   const double g = (gamma != gamma) ? 10.0 * kEps64 : gamma;  // NaN: not given; negative: never gates
-  // per-channel W', dW' staging [ns, n] each
+  SsqCwtParams S;
+  memset(&S, 0, sizeof(S));
+  S.ns = (int)ns;
+  S.n = n;
+  S.gate = (float)(g / K);
+  S.gate2 = g < 0.0 ? 0.f : (float)std::min((g / K) * (g / K), 3.0e38);
+  S.is_log = is_log;
+  S.f0 = (float)f0;
+  S.inv_step = (float)inv_step;
+  S.flipud = (flags & SSQ_FLAG_NO_FLIPUD) ? 0 : 1;
+  S.squeezing = squeezing == SSQ_SQUEEZE_LEBESGUE ? SSQ_SQUEEZE_LEBESGUE : SSQ_SQUEEZE_SUM;
+  S.K = (float)K;
+  S.leb_val = (float)(1.0 / (double)ns);
   const size_t stage = (size_t)ns * n * sizeof(float2);
-  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, stage));
-  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux1, stage));
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   SSQ_TRY(cwt_forward(ctx, c, log2L, pl, lo, hi, tw_s, xhat, ws0, ws1));
   SSQ_CUDA_TRY(ctx, cudaMemsetAsync(d_Tx, 0, (size_t)channels * stage, ctx->stream));
+  if (cwt_fused_ok(ctx, pl, n)) {
+    // one sweep over all (channel, scale) row pairs: the last pass of every pair reassigns straight into Tx
+    // the fused epilogue sees the rows before the 1/L of the inverse transform: fold it into K and the gate
+    S.Tx = (float2*)d_Tx;
+    S.K = (float)(K / (double)L);
+    S.gate = (float)(g / K * (double)L);
+    S.gate2 = g < 0.0 ? 0.f : (float)std::min((g / K * (double)L) * (g / K * (double)L), 3.0e38);
+    S.aux_kb = d_kb;
+    S.aux_w = d_w;
+    if (d_kb) SSQ_CUDA_TRY(ctx, cudaMemsetAsync(d_kb, 0xff, (size_t)channels * ns * n * sizeof(int), ctx->stream));
+    SSQ_TRY(cwt_inverse_rows(ctx, c, log2L, pl, lo, hi, tw_s, xhat, d_scales, 2, nullptr, nullptr, n, (L - n) / 2,
+                             (float)(1.0 / (double)L), 0, channels * ns * 2, ws0, ws1, max_rows, &S));
+    SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ev_valid = true;
+    ctx->last_kernel = "fft128_pass_kernel<fused ssq_cwt>";
+    return SSQ_OK;
+  }
+  // per-channel W', dW' staging [ns, n] each, then the stand-alone reassignment
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, stage));
+  SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux1, stage));
   for (int64_t ch = 0; ch < channels; ++ch) {
     // rows of channel ch; outputs land at row (cs - ch*ns) of the staging buffers
     float2* W = (float2*)ctx->ws_aux0.p - (size_t)ch * ns * n;
     float2* D = (float2*)ctx->ws_aux1.p - (size_t)ch * ns * n;
     SSQ_TRY(cwt_inverse_rows(ctx, c, log2L, pl, lo, hi, tw_s, xhat, d_scales, 2, W, D, n, (L - n) / 2,
                              (float)(1.0 / (double)L), ch * ns * 2, (ch + 1) * ns * 2, ws0, ws1, max_rows));
-    SsqCwtParams S;
-    memset(&S, 0, sizeof(S));
     S.W = (const float2*)ctx->ws_aux0.p;
     S.D = (const float2*)ctx->ws_aux1.p;
     S.Tx = (float2*)d_Tx + (size_t)ch * ns * n;
-    S.ns = (int)ns;
-    S.n = n;
-    S.gate = (float)(g / K);
-    S.is_log = is_log;
-    S.f0 = (float)f0;
-    S.inv_step = (float)inv_step;
-    S.flipud = (flags & SSQ_FLAG_NO_FLIPUD) ? 0 : 1;
-    S.squeezing = squeezing == SSQ_SQUEEZE_LEBESGUE ? SSQ_SQUEEZE_LEBESGUE : SSQ_SQUEEZE_SUM;
-    S.K = (float)K;
-    S.leb_val = (float)(1.0 / (double)ns);
+    S.aux_kb = d_kb ? d_kb + (size_t)ch * ns * n : nullptr;
+    S.aux_w = d_w ? d_w + (size_t)ch * ns * n : nullptr;
     ssq_cwt_reassign_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(S);
     SSQ_TRY(ssq_check_launch(ctx, "ssq_cwt_reassign_kernel"));
   }
@@ -405,6 +469,14 @@ extern "C" ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int6
   ctx->ev_valid = true;
   ctx->last_kernel = "fft128_pass_kernel+ssq_cwt_reassign_kernel";
   return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_ssq_cwt_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
+                                            int64_t x_stride, int wavelet, const double* scales, int64_t ns,
+                                            double dt, int freq_dist, int padtype, int squeezing, int maprange,
+                                            double gamma, unsigned flags, float* d_Tx, double* ssq_freqs) {
+  return ssq_ssq_cwt_batch_diag_f32(ctx, d_x, channels, n, x_stride, wavelet, scales, ns, dt, freq_dist, padtype,
+                                    squeezing, maprange, gamma, flags, d_Tx, ssq_freqs, nullptr, nullptr);
 }
 
 extern "C" ssq_status ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet, const double* scales,
@@ -428,7 +500,8 @@ extern "C" ssq_status ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int 
 
 extern "C" ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet, const double* scales,
                                       int64_t ns, double dt, int freq_dist, int padtype, int squeezing, int maprange,
-                                      double gamma, unsigned flags, double* Tx, double* ssq_freqs) {
+                                      double gamma, unsigned flags, double* Tx, double* ssq_freqs, double* w,
+                                      int32_t* kb) {
   if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
   if (!x || !scales || !Tx) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
   SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -436,9 +509,18 @@ extern "C" ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, 
   const size_t cnt = (size_t)ns * n;
   SSQ_TRY(upload_f64_as_f32(ctx, x, (size_t)n, ctx->ws_in));
   SSQ_TRY(devbuf_reserve(ctx, ctx->ws_out, cnt * sizeof(float2)));
-  SSQ_TRY(ssq_ssq_cwt_batch_f32(ctx, (const float*)ctx->ws_in.p, 1, n, n, wavelet, scales, ns, dt, freq_dist,
-                                padtype, squeezing, maprange, gamma, flags, (float*)ctx->ws_out.p, ssq_freqs));
-  return download_f32_as_f64(ctx, ctx->ws_out.p, cnt * 2, Tx);
+  if (w) SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux2, cnt * sizeof(float)));
+  if (kb) SSQ_TRY(devbuf_reserve(ctx, ctx->ws_misc, cnt * sizeof(int)));
+  SSQ_TRY(ssq_ssq_cwt_batch_diag_f32(ctx, (const float*)ctx->ws_in.p, 1, n, n, wavelet, scales, ns, dt, freq_dist,
+                                     padtype, squeezing, maprange, gamma, flags, (float*)ctx->ws_out.p, ssq_freqs,
+                                     w ? (float*)ctx->ws_aux2.p : nullptr, kb ? (int*)ctx->ws_misc.p : nullptr));
+  SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_out.p, cnt * 2, Tx));
+  if (w) SSQ_TRY(download_f32_as_f64(ctx, ctx->ws_aux2.p, cnt, w));
+  if (kb) {
+    SSQ_CUDA_TRY(ctx, cudaMemcpyAsync(kb, ctx->ws_misc.p, cnt * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SSQ_OK;
 }
 
 // icwt: cwt.rs:548-718, one-integral branch only.

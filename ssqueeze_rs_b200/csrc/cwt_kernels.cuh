@@ -17,6 +17,101 @@
 #include "ssq_common.cuh"
 #include "fft_regs.cuh"
 
+// ------------------------------------------------------------------------------------
+// ssq_cwt reassignment (ssq_cwt.rs:116-222 + phase_cwt :15-47).
+// W, D: already scaled by 1/L, psi-hat peak-normalised: true Wx = W * K.
+// ------------------------------------------------------------------------------------
+struct SsqCwtParams {
+  const float2* W;    // [ns, n] (stand-alone kernel only)
+  const float2* D;
+  float2* Tx;         // stand-alone: [ns, n] of one channel; fused: [channels, ns, n]; zero-initialised
+  int ns;
+  int64_t n;
+  float gate;         // gamma / K (in the units of the W handed to ssq_cwt_item): |W| < gate -> skipped
+  float gate2;        // gate^2, clamped to [0, 3e38] (the fast path compares squared magnitudes)
+  int is_log;
+  float f0, inv_step; // lin: (w - f0) * inv_step ; log: (log2 w - f0) * inv_step
+  int flipud, squeezing;
+  float K, leb_val;
+  int* aux_kb;        // optional diagnostics, same layout as Tx: destination row per (scale, column), -1 = nothing added
+  float* aux_w;       // optional: w (Hz), +inf where gated
+};
+
+// Rare magnitudes (|W|^2 outside fp32's comfortable range): the scale-free ratio after an exact power-of-two
+// rescale, and the gate on the true magnitude.  Out of line: the hot path below must stay short.
+__device__ __noinline__ float ssq_cwt_w_slow(float2 Wv, float2 Dv, float gate) {
+  const float mag = hypotf(Wv.x, Wv.y);
+  if (mag < gate) return __int_as_float(0x7f800000);  // gated (ssq_cwt.rs:29-30)
+  float c = Wv.x, d = Wv.y, a = Dv.x, bb = Dv.y;
+  if (mag < 1e-15f) {
+    const float up = 1.8446744e19f;  // 2^64
+    c *= up; d *= up; a *= up; bb *= up;
+  } else if (mag > 1e15f) {
+    const float dn = 5.4210109e-20f;  // 2^-64
+    c *= dn; d *= dn; a *= dn; bb *= dn;
+  }
+  return fabsf((bb * c - a * d) / ((c * c + d * d) * 6.283185307179586f));
+}
+
+// One (scale, column) item: returns the destination row of Tx, or -1 when nothing is added (gated, w not finite,
+// bin outside the grid: ssq_cwt.rs:29-30, :167-169, :177-179).  w_out: the phase transform (+inf when gated).
+// Wv, Dv may carry any common positive factor (the ratio is scale-free); P.gate is expressed in their units.
+__device__ __forceinline__ int ssq_cwt_item(const SsqCwtParams& P, float2 Wv, float2 Dv, float& w_out) {
+  const float c = Wv.x, d = Wv.y;
+  const float m2 = fmaf(c, c, d * d);
+  float w;
+  if (m2 > 1e-30f && m2 < 1e30f && m2 >= P.gate2) {  // (gate2 = gate^2 clamped into the fp32 range by the host)
+    const float num = fmaf(Dv.y, c, -Dv.x * d);  // Im(dW conj W)
+    w = fabsf(num) * __frcp_rn(m2 * 6.283185307179586f);
+  } else {
+    w = ssq_cwt_w_slow(Wv, Dv, P.gate);
+  }
+  w_out = w;
+  if (!(w <= 3.4028235e38f)) return -1;  // gated / inf / NaN skipped (:167-169)
+  const float v = P.is_log ? (log2f(w) - P.f0) * P.inv_step : (w - P.f0) * P.inv_step;
+  // f64::round, half away from zero (:176, :187): floor(v + 1/2) for v > -1/2 (values in (-1/2, 0) round to -0 ->
+  // bin 0), anything at or below -1/2 is a negative bin: dropped
+  const float r = floorf(v + 0.5f);
+  if (!(v > -0.5f && r < (float)P.ns)) return -1;  // out of range dropped (:177-179); NaN fails the first test
+  const int bin = (int)r;
+  return P.flipud ? P.ns - 1 - bin : bin;
+}
+
+// Stand-alone reassignment (the path taken when the last FFT pass cannot carry the fused epilogue): one thread per
+// time column; the thread is the only writer of its Tx column, so the accumulation runs in ascending scale order
+// (the reference's order).
+__global__ void ssq_cwt_reassign_kernel(const SsqCwtParams P) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.n) return;
+  const float2* __restrict__ Wc = P.W + b;
+  const float2* __restrict__ Dc = P.D + b;
+  float2* Tc = P.Tx + b;
+  // the W, D values of eight scales are in flight at once, and the thread adds to Tx with a reduction (no value
+  // returned: nothing to wait for; same-thread reductions to one address stay in program order)
+  constexpr int U = 8;
+  for (int i0 = 0; i0 < P.ns; i0 += U) {
+    float2 Wb[U], Db[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(i0 + u, P.ns - 1);
+      Wb[u] = __ldcs(Wc + (size_t)i * P.n);
+      Db[u] = __ldcs(Dc + (size_t)i * P.n);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u >= P.ns) break;
+      float w;
+      const int k = ssq_cwt_item(P, Wb[u], Db[u], w);
+      if (P.aux_kb) P.aux_kb[(size_t)(i0 + u) * P.n + b] = k;
+      if (P.aux_w) P.aux_w[(size_t)(i0 + u) * P.n + b] = w;
+      if (k < 0) continue;
+      float2* t = Tc + (size_t)k * P.n;
+      if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) atomicAdd(&t->x, P.leb_val);
+      else atomicAdd(t, make_float2(Wb[u].x * P.K, Wb[u].y * P.K));
+    }
+  }
+}
+
 struct FftPass {
   const float2* in;   // [rows, L] (unused by the first pass' functor loads)
   float2* out;        // [rows, L] (unused by the last pass' functor stores)
@@ -38,12 +133,14 @@ struct FftPass {
   float inv_dt;
   int up_shift;       // mode 2: 7 * (number of leading passes skipped as broadcasts), see cwt_host.inl
   // ---- store functor ------------------------------------------------------------
-  int store_mode;     // 0 plain, 1 final: scaled, unpadded rows to outW / outD
+  int store_mode;     // 0 plain, 1 final: scaled, unpadded rows to outW / outD, 2: fused ssq_cwt epilogue
   float2* outW;       // [channels, ns, out_cols]
   float2* outD;       // [channels, ns, out_cols] (may be NULL)
   int64_t out_cols, n1;  // out_cols = n (unpadded) or L (rpadded, n1 = 0)
   float out_scale;    // K / L   (K = de-normalisation constant of psi-hat)
   int l2_norm;
+  // ---- fused ssq_cwt epilogue (store_mode 2, fft128_pass_kernel<TC, true> only) ------------------
+  SsqCwtParams E;     // E.Tx: [channels, ns, n]
 };
 
 // GMW(gamma=3, beta=60) is evaluated as exp(60 ln w - w^3 - SSQ_GMW_LOGPEAK): peak 1
@@ -255,25 +352,69 @@ __device__ __forceinline__ float2 tw_fwd(const FftPass& P, int64_t e) {  // W_L^
   return cmulf(__ldg(P.tw_lo + lo), __ldg(P.tw_hi + hi));
 }
 
-template <int TC>  // TC adjacent columns per CTA (32 or 64): TC * 8 B contiguous per global access, 8 * TC threads
+// FUSED (the last pass of ssq_cwt, ssq_cwt.rs:365-480 in one pass over the scales): the CTA works on the W row and
+// the dW row of ONE scale at once -- adjacent lanes (2 col, 2 col + 1) carry the same column of the two rows, so after
+// the second butterfly a lane pair swaps halves (8 shuffles) and each lane holds Wx and dWx of 8 outputs: phase
+// transform, bin and the update of Tx happen straight from the registers; Wx / dWx are never written.  The update is
+// a vector reduction (red.global.add.v2.f32): several scales may hit one Tx element from different CTAs, so the
+// order of additions inside an element is not fixed (rounding-level; the bins are).
+template <int TC, bool FUSED = false>  // TC adjacent columns per CTA (32 or 64): TC * 8 B contiguous per global access, 8 * TC threads
 __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   extern __shared__ float2 buf[];  // [TC * 129]
   __shared__ float2 w128[128];  // W_128^m
-  const int c = threadIdx.x % TC, g = threadIdx.x / TC;
+  const int cfull = threadIdx.x % TC, g = threadIdx.x / TC;
+  const int which_l = FUSED ? (cfull & 1) : 0;      // FUSED: 0 = W row, 1 = dW row
+  const int c = FUSED ? (cfull >> 1) : cfull;       // column inside the CTA
+  constexpr int CW = FUSED ? TC / 2 : TC;           // columns per CTA
   if (threadIdx.x < 128) w128[threadIdx.x] = tw_fwd(P, (int64_t)threadIdx.x << (P.log2L - 7));
   // in-row indices are 32-bit (L <= 2^27, checked on the host): the passes are issue-bound and 64-bit
   // index arithmetic was a fifth of their instructions
   const int L = 1 << P.log2L;
   const int Q = L >> 7;
   const int Ns = 1 << P.log2Ns;
-  const int row = blockIdx.y;
-  const int j0 = blockIdx.x * TC, j = j0 + c;
+  const int row = FUSED ? 2 * (int)blockIdx.y + which_l : (int)blockIdx.y;
+  const int j0 = blockIdx.x * CW, j = j0 + c;
   const int kk = j & (Ns - 1);
   const int twshift = P.log2L - P.log2Ns - 7;  // W_{128 Ns}^e = W_L^(e << twshift)
   const bool inv = P.sign > 0;
 
   float2 v[16];
-  if (P.load_mode == 2) {
+  // Pruned generation (band-limited rows whose leading passes were skipped, up_shift >= 6): input t of EVERY column of
+  // the CTA is the same spectrum bin (j0 >> S) + t (Q >> S), so the 128 products x-hat psi-hat are evaluated once per
+  // CTA (per row of the pair when FUSED) into shared memory instead of 16 times per thread: expf / logf and the index
+  // logic were 35 % of these passes (ncu r2f).
+  __shared__ float2 ytab[FUSED ? 256 : 128];
+  const bool shared_gen = P.load_mode == 2 && P.up_shift >= 6 && P.up_shift <= P.log2L - 7;
+  if (shared_gen) {
+    if (threadIdx.x < (FUSED ? 256 : 128)) {
+      const int t = threadIdx.x & 127;
+      const int wrow = FUSED ? 2 * (int)blockIdx.y + (int)(threadIdx.x >> 7) : (int)blockIdx.y;
+      const unsigned gr = (unsigned)P.row0 + (unsigned)wrow;
+      const unsigned cs = gr / (unsigned)P.nd;
+      const int which = (int)(gr - cs * (unsigned)P.nd);
+      const unsigned chn = cs / (unsigned)P.ns;
+      const float scale = __ldg(P.scales + (int)(cs - chn * (unsigned)P.ns));
+      const int idx = (j0 >> P.up_shift) + t * (Q >> P.up_shift);
+      float2 x = make_float2(0.f, 0.f);
+      if (idx <= (L >> 1)) {  // negative frequencies: psi-hat = 0 (cwt.rs:496-541)
+        const float xi = (6.283185307179586f * (float)idx) * (1.f / (float)L);
+        const float ps = psihat(P.wavelet, scale * xi);
+        if (ps != 0.f) {
+          const float2 h = __ldg(P.xhat + (size_t)chn * L + idx);
+          x = make_float2(h.x * ps, h.y * ps);
+          if (which == 1) {  // * i*xi/dt (cwt.rs:205-209, ssq_cwt.rs:374-377)
+            const float f = xi * P.inv_dt;
+            x = make_float2(-x.y * f, x.x * f);
+          }
+        }
+      }
+      if (inv) x.y = -x.y;
+      ytab[threadIdx.x] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = ytab[(FUSED ? 128 * which_l : 0) + g + 8 * u];
+  } else if (P.load_mode == 2) {
     // x-hat * psi-hat generated on the fly: the row's constants once per thread, and an exact integer
     // early-out -- psihat() returns 0 beyond its cut-off, i.e. for spectrum indices >= blim
     // 32-bit row arithmetic (the host refuses more than 2^31 rows): three 64-bit divisions per thread were
@@ -351,13 +492,13 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
     for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmulf(v[k1], w128[(g * k1) & 127]);
   }
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) buf[(k1 * 8 + g) * TC + c] = v[k1];
+  for (int k1 = 0; k1 < 16; ++k1) buf[(k1 * 8 + g) * TC + cfull] = v[k1];
   __syncthreads();
   float2 a[8], b[8];
 #pragma unroll
   for (int gg = 0; gg < 8; ++gg) {
-    a[gg] = buf[(g * 8 + gg) * TC + c];        // k1 = h = g
-    b[gg] = buf[((g + 8) * 8 + gg) * TC + c];  // k1 = h + 8
+    a[gg] = buf[(g * 8 + gg) * TC + cfull];        // k1 = h = g
+    b[gg] = buf[((g + 8) * 8 + gg) * TC + cfull];  // k1 = h + 8
   }
   fft8_fwd(a);  // a[k2] = Y[g + 16 k2]
   fft8_fwd(b);  // b[k2] = Y[g + 8 + 16 k2]
@@ -367,6 +508,38 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
       a[k2].y = -a[k2].y;
       b[k2].y = -b[k2].y;
     }
+  }
+  if constexpr (FUSED) {
+    // even lane (W row): keeps a = W[k1 = g], receives the dW row's a; odd lane: keeps b = dW[k1 = g + 8], receives
+    // the W row's b.  Each lane then owns 8 outputs o = base + (koff + 16 k2) Ns with both values.
+    const unsigned gr = (unsigned)P.row0 + 2u * blockIdx.y;  // the W row; rows are ordered (channel, scale, which)
+    const unsigned cs = gr >> 1;                              // channel * ns + scale
+    const unsigned chn = cs / (unsigned)P.ns;
+    // (the 1/L of the inverse transform is folded into E.K and E.gate by the host: the phase ratio is scale-free)
+    const int base = ((j - kk) << 7) + kk - (int)P.n1;
+    const int koff = g + 8 * which_l;
+    float2* Tch = P.E.Tx + (size_t)chn * P.E.ns * P.E.n;
+    const size_t drow = (size_t)cs * P.E.n;  // diagnostics: [channels, ns, n]
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      const float2 send = which_l ? a[k2] : b[k2];
+      float2 recv;
+      recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+      recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+      const float2 Wr = which_l ? recv : a[k2], Dr = which_l ? b[k2] : recv;
+      const int col = base + (koff + 16 * k2) * Ns;
+      if ((unsigned)col >= (unsigned)P.E.n) continue;
+      const float2 Wv = Wr, Dv = Dr;
+      float w;
+      const int k = ssq_cwt_item(P.E, Wv, Dv, w);
+      if (P.E.aux_kb) P.E.aux_kb[drow + col] = k;
+      if (P.E.aux_w) P.E.aux_w[drow + col] = w;
+      if (k < 0) continue;
+      float2* t = Tch + (size_t)k * P.E.n + col;
+      if (P.E.squeezing == SSQ_SQUEEZE_LEBESGUE) atomicAdd(&t->x, P.E.leb_val);
+      else atomicAdd(t, make_float2(Wv.x * P.E.K, Wv.y * P.E.K));
+    }
+    return;
   }
   // store functor with the row's constants hoisted (the per-element version divides 64-bit indices)
   float2* sdst = P.out + (size_t)row * L;
@@ -425,73 +598,6 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
     }
   }
 }
-
-// ------------------------------------------------------------------------------------
-// ssq_cwt reassignment (ssq_cwt.rs:116-222 + phase_cwt :15-47): one thread per time
-// column; the thread is the only writer of its Tx column, so the accumulation is
-// a plain read-modify-write in ascending scale order (the reference's order).
-// W, D: [ns, n] (already scaled by 1/L, psi-hat peak-normalised: true Wx = W * K).
-// ------------------------------------------------------------------------------------
-struct SsqCwtParams {
-  const float2* W;
-  const float2* D;
-  float2* Tx;         // [ns, n] zero-initialised
-  int ns;
-  int64_t n;
-  float gate;         // gamma / K : |W| < gate -> skipped
-  int is_log;
-  float f0, inv_step; // lin: (w - f0) * inv_step ; log: (log2 w - f0) * inv_step
-  int flipud, squeezing;
-  float K, leb_val;
-};
-
-__global__ void ssq_cwt_reassign_kernel(const SsqCwtParams P) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= P.n) return;
-  const float2* __restrict__ Wc = P.W + b;
-  const float2* __restrict__ Dc = P.D + b;
-  float2* Tc = P.Tx + b;
-  // The loop used to be one latency chain per scale (load W, D -> bin -> load Tx -> store Tx, in program order
-  // because Tx may alias W / D for the compiler): 2.9 ms per channel for 11.9 GB.  Now the W, D values of eight
-  // scales are in flight at once, and the thread -- the only writer of its column -- adds to Tx with a reduction
-  // (no value returned: nothing to wait for; same-thread reductions to one address stay in program order).
-  constexpr int U = 8;
-  for (int i0 = 0; i0 < P.ns; i0 += U) {
-    float2 Wb[U], Db[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = min(i0 + u, P.ns - 1);
-      Wb[u] = __ldcs(Wc + (size_t)i * P.n);
-      Db[u] = __ldcs(Dc + (size_t)i * P.n);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (i0 + u >= P.ns) break;
-      const float2 Wv = Wb[u], Dv = Db[u];
-      const float mag = hypotf(Wv.x, Wv.y);
-      if (mag < P.gate) continue;  // ssq_cwt.rs:29-30
-      float c = Wv.x, d = Wv.y, a = Dv.x, bb = Dv.y;
-      if (mag < 1e-15f) {  // keep c*c+d*d away from fp32 underflow; the ratio is scale-free
-        const float up = 1.8446744e19f;  // 2^64
-        c *= up; d *= up; a *= up; bb *= up;
-      } else if (mag > 1e15f) {
-        const float dn = 5.4210109e-20f;  // 2^-64
-        c *= dn; d *= dn; a *= dn; bb *= dn;
-      }
-      const float w = fabsf((bb * c - a * d) / ((c * c + d * d) * 6.283185307179586f));
-      if (!(w <= 3.4028235e38f)) continue;  // inf / NaN skipped (:167-169)
-      const float v = P.is_log ? (log2f(w) - P.f0) * P.inv_step : (w - P.f0) * P.inv_step;
-      const float r = roundf(v);  // f64::round: half away from zero (:176, :187)
-      if (!(r >= 0.f && r < (float)P.ns)) continue;  // out of range dropped (:177-179)
-      const int bin = (int)r;
-      const int k = P.flipud ? P.ns - 1 - bin : bin;
-      float2* t = Tc + (size_t)k * P.n;
-      if (P.squeezing == SSQ_SQUEEZE_LEBESGUE) atomicAdd(&t->x, P.leb_val);
-      else atomicAdd(t, make_float2(Wv.x * P.K, Wv.y * P.K));
-    }
-  }
-}
-
 
 // ------------------------------------------------------------------------------------
 // icwt, one-integral branch (cwt.rs:590-627): x[c][j] = final_norm * sum_i Re Wx[c][i][j] * norm_i + x_mean,
