@@ -37,11 +37,30 @@ N_FFT, HOP = 512, 32
 CHANNELS = 384
 SAMPLES = 1_800_000
 WORKLOAD = "ssq_stft 384ch x 1.8M samples (60 s @ 30 kHz) synthetic neural, n_fft=512 hop=32 hann reflect"
-# dram__bytes_read.sum + dram__bytes_write.sum of one 384-channel launch of the dominant kernel, from the ncu
-# pass over this same command (profiles/r1q_bench_launches.csv: 5.9 GB read + 47.2 GB written; the
-# algorithmic figure is 2.76 + 44.41 GB; the r1k capture earlier in the round read 3.79 + 45.37 GB).
-# Only valid for the default workload; null otherwise.
-NCU_DRAM_BYTES_PER_LAUNCH = 53.1e9
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel on the default workload, from
+    the ncu pass recorded in profiles/bench_dram.json by tools/record_dram.py (which stores the commit it was taken
+    at).  (None, why) when the record is missing or was taken on another kernel build."""
+    path = os.path.join(ROOT, "profiles", "bench_dram.json")
+    try:
+        rec = json.load(open(path))
+        return float(rec["dram_bytes_per_launch"]), {"file": "profiles/bench_dram.json", "commit": rec.get("commit"),
+                                                     "kernel_sources_sha": rec.get("kernel_sources_sha"),
+                                                     "current_kernel_sources_sha": kernel_sources_sha()}
+    except Exception as e:  # noqa: BLE001
+        return None, {"unavailable": str(e)}
+
+
+def kernel_sources_sha():
+    """Fingerprint of the CUDA sources the benchmarked kernel is built from (so a stale ncu record shows)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "ssqueeze_rs_b200", "csrc")
+    for f in ("stft_h32r.cuh", "fft_regs.cuh", "stft_kernels.cuh", "ssq_common.cuh"):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def algorithmic_bytes(channels, n, n_fft=N_FFT, hop=HOP):
@@ -226,6 +245,222 @@ def parity_gates(eng, torch, dev, n_samples=200_000):
     return rep
 
 
+# ---------------------------------------------------------------------------------------------------------
+# The other named configs of BASELINE.json, as sub-records of the same JSON line (`configs`): device-timed,
+# channels sharded over the ranks (strong scaling), each with its own roofline, a parity check of the CUDA path
+# against the oracle on a cut, and a CPU baseline (rank 0 of a 1-GPU run only).
+# ---------------------------------------------------------------------------------------------------------
+def _timed(torch, stream, step, warmup, steps, dev):
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            step()
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / steps
+
+
+def _record(name, units_rank, ms_rank, abytes_rank, dev, world, desc, kernel, extra):
+    """Per-rank figures of one side config; side_configs() turns them into the job's record (collectives there, so
+    that a rank that failed cannot leave the others waiting inside an all-reduce)."""
+    return dict(name=name, units=units_rank, ms=ms_rank, abytes=abytes_rank, desc=desc, kernel=kernel, extra=extra)
+
+
+def _finish_record(r, dev, world):
+    from ssqueeze_rs_b200.dist import job_throughput, sum_over_ranks
+    name, units_rank, ms_rank, abytes_rank, desc, kernel, extra = (r[k] for k in ("name", "units", "ms", "abytes", "desc", "kernel", "extra"))
+    per_s, ms = job_throughput(units_rank, ms_rank, dev)
+    ab = sum_over_ranks(abytes_rank, dev)
+    peak, peak_src = measured_peak_gbs()
+    ach = ab / (ms * 1e-3) / 1e9 / world  # per GPU
+    rec = {"metric": f"{name} input Msamples/s", "value": per_s / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+           "scaling": "strong", "config": {"workload": desc},
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_step": ab,
+                        "note": "per GPU; whole step (all kernels of the call), not one kernel"},
+           "kernel": kernel}
+    rec.update(extra)
+    return rec
+
+
+def side_c5(torch, eng, dev, rank, world, stream, g, cpu, scale=1.0):
+    """BASELINE configs[4]: 1024 channels x 10 min @ 30 kHz (18 M samples), 1024 / world channels per GPU, input
+    resident (73.7 GB at world 1), Tx through a ring of two 16-channel output buffers as a host gather would drain
+    them.  Input: white noise + two tones (the neural recipe needs an 18 M-point FFT per channel block to generate)."""
+    from oracle import parity as P
+    from oracle import ssq_oracle as O
+    ch_total, n = max(world, int(1024 * scale)), int(18_000_000 * (scale if scale < 1 else 1))
+    c0, c1 = ch_total * rank // world, ch_total * (rank + 1) // world
+    ch, blk = c1 - c0, 16
+    win = np.hanning(N_FFT)
+    x = torch.empty((ch, n), dtype=torch.float32, device=dev)
+    tt = torch.arange(n, device=dev, dtype=torch.float32) / FS
+    tone = 20.0 * torch.sin(2 * np.pi * 8.0 * tt) + 5.0 * torch.sin(2 * np.pi * 60.0 * tt)
+    for b0 in range(0, ch, blk):
+        x[b0:b0 + blk] = torch.randn((min(blk, ch - b0), n), generator=g, device=dev) * 10 + tone
+    del tt, tone
+    nfr = (n - 1) // HOP + 1
+    ring = [torch.empty((blk, N_FFT // 2 + 1, nfr), dtype=torch.complex64, device=dev) for _ in range(2)]
+
+    def step():
+        for i, b0 in enumerate(range(0, ch, blk)):
+            m = min(blk, ch - b0)
+            eng.ssq_stft(x[b0:b0 + m], win, N_FFT, HOP, FS, out=ring[i & 1][:m])
+
+    ms = _timed(torch, stream, step, 1, 2, dev)
+    extra = {}
+    if rank == 0:
+        # parity: slices of frames at the start, far into and at the end of the recording (a frame depends on its own
+        # 512 samples only), every bin classified
+        tot = dict(bins_total=0, mismatch_total=0, within_edge=0, ill_conditioned=0, below_energy_gate=0, unexplained=0,
+                   max_err_over_tol=0.0)
+        left = (N_FFT - 1) // 2
+        for f0, nf in ((0, 64), (nfr // 2, 64), (nfr - 64, 64)):
+            g0 = max(0, (f0 * HOP - left) // HOP)
+            a, b = g0 * HOP, min(n, (f0 + nf - 1) * HOP - left + N_FFT)
+            xs = x[0:1, a:b].contiguous()
+            Tx, aux = eng.ssq_stft(xs, win, N_FFT, HOP, FS, return_aux=True)
+            _, _, ao = O.ssq_stft(xs[0].cpu().numpy().astype(np.float64), win, n_fft=N_FFT, hop_len=HOP, fs=FS, return_aux=True)
+            r = P.classify_stft_bins(aux["kb"][0].cpu().numpy(), ao, N_FFT, FS, None, w_dev=aux["w"][0].cpu().numpy().astype(np.float64))
+            for k in tot:
+                tot[k] = max(tot[k], r[k]) if k == "max_err_over_tol" else tot[k] + r[k]
+        tot["against"] = "oracle/ssq_oracle.py on three 64-frame slices of channel 0 (start, middle, end)"
+        extra["parity"] = tot
+        if cpu:
+            msps, threads, sec = cpu_reference_run(450_000, 1, 0, mode=0)
+            extra["cpu_baseline"] = {"value": msps, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                                     "sample": f"1 channel x 450000 samples ({sec:.1f} s), C restatement of ssq_stft.rs as written"}
+    rec = _record("ssq_stft(c5)", float(ch) * n, ms, algorithmic_bytes(ch, n), dev, world,
+                  f"ssq_stft configs[4]: {ch_total}ch x {n} samples over {world} GPU(s), blocks of {blk} channels through a "
+                  f"ring of 2 output buffers, n_fft=512 hop=32; white noise + tones", eng.last_kernel_name(), extra)
+    del x, ring
+    torch.cuda.empty_cache()
+    return rec
+
+
+def side_c4_istft(torch, eng, dev, rank, world, stream, g, cpu, scale=1.0):
+    """BASELINE configs[3]: istft on 4096 channels x 10 s @ 30 kHz (300 k samples), n_fft=512 hop=32 (overlap-add +
+    window norm + unpad); Sx produced on the device by the stft kernel (78.9 GB at world 1)."""
+    from oracle import ssq_oracle as O
+    ch_total, n = max(world, int(4096 * scale)), 300_000
+    c0, c1 = ch_total * rank // world, ch_total * (rank + 1) // world
+    ch = c1 - c0
+    win = np.hanning(N_FFT)
+    x = torch.randn((ch, n), generator=g, device=dev) * 10
+    nfr = (n - 1) // HOP + 1
+    Sx = torch.empty((ch, N_FFT // 2 + 1, nfr), dtype=torch.complex64, device=dev)
+    for b0 in range(0, ch, 256):
+        eng.stft(x[b0:b0 + 256], win, N_FFT, HOP, out=Sx[b0:b0 + 256])
+    out = {}
+
+    def step():
+        out["x"] = eng.istft(Sx, win, N_FFT, HOP, N=n)
+
+    ms = _timed(torch, stream, step, 1, 3, dev)
+    extra = {}
+    if rank == 0:
+        xr = out["x"]
+        mae = float((xr - x).abs().mean())
+        So = Sx[0].cpu().numpy().astype(np.complex128)
+        xo = O.istft(So, win, n_fft=N_FFT, hop_len=HOP, N=n)
+        err = float(np.abs(xr[0].cpu().numpy() - xo).max() / np.abs(xo).max())
+        extra["parity"] = {"against": "oracle/ssq_oracle.py istft on channel 0 (same Sx)", "rel_max_err": err, "rtol": 1e-4,
+                           "within_rtol": bool(err < 1e-4), "round_trip_mae_all_channels": mae,
+                           "round_trip_mae_rel": mae / float(x.abs().mean())}
+        if cpu:
+            t0 = time.perf_counter()
+            O.istft(So, win, n_fft=N_FFT, hop_len=HOP, N=n)
+            sec = time.perf_counter() - t0
+            extra["cpu_baseline"] = {"value": n / sec / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                                     "sample": f"1 channel x {n} samples ({sec:.2f} s), NumPy oracle (pocketfft irfft + overlap-add loop); "
+                                               "the reference crate has no istft"}
+    rec = _record("istft", float(ch) * n, ms, ch * (4 * n + 8 * (N_FFT // 2 + 1) * nfr), dev, world,
+                  f"istft configs[3]: {ch_total}ch x {n} samples over {world} GPU(s), n_fft=512 hop=32", eng.last_kernel_name(), extra)
+    del x, Sx, out
+    torch.cuda.empty_cache()
+    return rec
+
+
+def side_c3_ssq_cwt(torch, eng, dev, rank, world, stream, g, cpu, scale=1.0):
+    """BASELINE configs[2]: ssq_cwt GMW nv=32 (576 scales) on 64 channels x 2^20 chirp+noise; Tx (4.8 GB per channel)
+    through a ring of two 4-channel output buffers."""
+    from oracle import parity as P
+    from oracle import ssq_oracle as O
+    ch_total, n = max(world, int(64 * scale)), 1 << 20
+    c0, c1 = ch_total * rank // world, ch_total * (rank + 1) // world
+    ch, blk = c1 - c0, 4
+    t = torch.arange(n, device=dev, dtype=torch.float64) / n
+    chirp = torch.sin(2 * np.pi * n * (0.001 * t + 0.5 * 0.399 * t * t)).to(torch.float32)
+    x = chirp.view(1, -1) + 0.5 * torch.randn((ch, n), generator=g, device=dev)
+    sc = eng.default_scales(n, 32)
+    ns = len(sc)
+    ring = [torch.empty((blk, ns, n), dtype=torch.complex64, device=dev) for _ in range(2)]
+
+    def step():
+        for i, b0 in enumerate(range(0, ch, blk)):
+            m = min(blk, ch - b0)
+            eng.ssq_cwt(x[b0:b0 + m], "gmw", sc, fs=1.0, nv=32, maprange="maximal", out=ring[i & 1][:m])
+
+    ms = _timed(torch, stream, step, 1, 2, dev)
+    kernel = eng.last_kernel_name()
+    extra = {}
+    del ring
+    torch.cuda.empty_cache()
+    if rank == 0:
+        # parity on a 2^16-sample cut of channel 0 (the float64 oracle needs 2 x ns x pad_len complex128: 80 GB at 2^20)
+        m = 1 << 16
+        xs = x[0:1, :m].contiguous()
+        Tx, sf, aux = eng.ssq_cwt(xs, "gmw", None, fs=1.0, nv=32, maprange="maximal", return_aux=True)
+        xs64 = xs[0].cpu().numpy().astype(np.float64)
+        t0 = time.perf_counter()
+        To, sfo, ao = O.ssq_cwt(xs64, "gmw", None, fs=1.0, nv=32, maprange="maximal", return_aux=True)
+        sec = time.perf_counter() - t0
+        kb = aux["kb"][0].cpu().numpy()
+        r = P.public(P.classify_cwt_bins(kb, ao, xs64, "gmw", 1.0, "reflect", sfo, w_dev=aux["w"][0].cpu().numpy().astype(np.float64)))
+        Tacc = P.reaccumulate_cwt(ao["Wx"], kb, To.shape[0])
+        r["Tx_rel_max_err_vs_reference_accumulation_over_device_rows"] = float(
+            np.abs(Tx[0].cpu().numpy().astype(np.complex128) - Tacc).max() / np.abs(To).max())
+        r["against"] = f"oracle/ssq_oracle.py ssq_cwt (f64) on a {m}-sample cut of channel 0, nv=32 ({To.shape[0]} scales)"
+        r["kernel"] = eng.last_kernel_name()
+        extra["parity"] = r
+        if cpu:
+            extra["cpu_baseline"] = {"value": m / sec / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                                     "sample": f"1 channel x {m} samples, {To.shape[0]} scales ({sec:.1f} s), NumPy oracle restating "
+                                               "ssq_cwt.rs (pocketfft); the full-size case needs > 80 GB in float64 (SURVEY 8a row 15)"}
+    rec = _record("ssq_cwt", float(ch) * n, ms, ch * (4 * n + 8 * ns * n), dev, world,
+                  f"ssq_cwt configs[2]: gmw nv=32 ({ns} scales), {ch_total}ch x {n} chirp+noise over {world} GPU(s), blocks of "
+                  f"{blk} channels through a ring of 2 output buffers", kernel, extra)
+    del x
+    torch.cuda.empty_cache()
+    return rec
+
+
+def side_configs(torch, eng, dev, rank, world, stream, cpu, scale=1.0):
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5351 + rank)
+    out = {}
+    from ssqueeze_rs_b200.dist import max_over_ranks
+    for key, fn in (("c5", side_c5), ("c4_istft", side_c4_istft), ("c3_ssq_cwt", side_c3_ssq_cwt)):
+        r, err = None, None
+        try:
+            r = fn(torch, eng, dev, rank, world, stream, g, cpu, scale)
+        except Exception as e:  # noqa: BLE001 -- a side record must not take the contract line down with it
+            torch.cuda.empty_cache()
+            err = f"{type(e).__name__}: {e}"
+        failed = max_over_ranks(0.0 if err is None else 1.0, dev)  # every rank takes part, whatever happened to it
+        if failed:
+            out[key] = {"error": err or "another rank failed"}
+        else:
+            out[key] = _finish_record(r, dev, world)
+    return out
+
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -316,8 +551,9 @@ def run_ours(args, rank, world, local_rank):
     kms = float(np.mean(kernel_ms))
     abytes = algorithmic_bytes(channels, n)
     achieved = abytes / (kms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic() if (channels, n) == (CHANNELS, SAMPLES) else (None, {"unavailable": "not the default workload"})
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (channels, n) == (CHANNELS, SAMPLES) else None, "kernel_ms": kms, "algorithmic_bytes_per_launch": abytes,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": abytes,
                 "peak_source": peak_src, "kernel": eng.last_kernel_name()}
 
     # ---- e2e through the host-buffer C-ABI call --------------------------------
@@ -337,6 +573,13 @@ def run_ours(args, rank, world, local_rank):
                         "as_intended_note": "same numerics, shared FFT plan, O(1) binning, parallel phase/reassign; "
                                             f"2 channels x 900000 samples ({sec_i:.1f} s)"}
 
+    configs = None
+    if not args.no_side_configs:
+        del x
+        torch.cuda.empty_cache()
+        configs = side_configs(torch, eng, dev, rank, world, stream, cpu=(world == 1 and not args.no_cpu_baseline),
+                               scale=args.side_scale)
+
     if rank == 0:
         line = {
             "metric": "ssq_stft input Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
@@ -346,7 +589,7 @@ def run_ours(args, rank, world, local_rank):
                        "hop": HOP, "fs": FS, "parallelism": f"channel-shard x{world}, no collective",
                        "l2_policy": "inputs (2.8 GB) and outputs (44 GB) per step exceed the 126 MB L2; no flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "checksum": chk,
+            "cpu_baseline": cpu_baseline, "parity": parity, "checksum": chk, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -515,6 +758,8 @@ def main():
     ap.add_argument("--samples", type=int, default=SAMPLES)
     ap.add_argument("--e2e-channels", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the c5 / c4_istft / c3_ssq_cwt sub-records")
+    ap.add_argument("--side-scale", type=float, default=1.0, help="shrink the side configs (channels, c5 length) for smoke runs")
     ap.add_argument("--ref-samples", type=int, default=450_000, help="samples per step of the reference arm")
     ap.add_argument("--n-fft", type=int, default=N_FFT, help="side workloads only: another STFT geometry")
     ap.add_argument("--hop", type=int, default=HOP)

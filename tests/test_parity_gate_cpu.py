@@ -31,7 +31,8 @@ def test_fp32_restatement_passes_the_gate(case):
     assert rep["unexplained"] == 0, P.public(rep)
     assert rep["max_err_over_tol"] < 0.6, P.public(rep)  # the derived bound holds with room, and is not vacuous
     # the device's Tx would equal the oracle's on every column without a flip
-    assert rep["mismatch_total"] <= rep["within_edge"] + rep["ill_conditioned"] + rep["gate_edge"]
+    assert rep["mismatch_total"] <= (rep["within_edge"] + rep["ill_conditioned"] + rep["gate_edge"]
+                                     + rep["below_energy_gate"])
 
 
 @pytest.mark.parametrize("rule", ["floor", "drop_out_of_range"])
