@@ -413,7 +413,7 @@ def side_c3_ssq_cwt(torch, eng, dev, rank, world, stream, g, cpu, scale=1.0):
     torch.cuda.empty_cache()
     if rank == 0:
         # parity on a 2^16-sample cut of channel 0 (the float64 oracle needs 2 x ns x pad_len complex128: 80 GB at 2^20)
-        m = 1 << 16
+        m = 1 << 17
         xs = x[0:1, :m].contiguous()
         Tx, sf, aux = eng.ssq_cwt(xs, "gmw", None, fs=1.0, nv=32, maprange="maximal", return_aux=True)
         xs64 = xs[0].cpu().numpy().astype(np.float64)
@@ -699,11 +699,23 @@ def run_other(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def _pinned_near(nbytes, device):
+    """Pinned host bytes on the GPU's NUMA node (ssq_host_alloc_near); returns (numpy uint8 view, address)."""
+    import ctypes as C
+    from ssqueeze_rs_b200._lib import load
+    p = C.c_void_p()
+    if load().ssq_host_alloc_near(C.byref(p), nbytes, device) != 0 or not p.value:
+        return None, None
+    return np.frombuffer((C.c_char * nbytes).from_address(p.value), dtype=np.uint8), p
+
+
 def run_e2e(eng, args, rank, world, window, x_dev, dev):
-    """Host pinned x -> [H2D, kernel, D2H] -> host pinned Tx, every step."""
+    """Host pinned x -> [H2D, kernel, D2H] -> host pinned Tx, every step; then the box's own ceiling for the
+    dominant transfer (plain D2H copies of the same size into the same buffers, all ranks at once)."""
     import torch
     import torch.distributed as dist
     import psutil
+    from ssqueeze_rs_b200._lib import load
     n = args.samples
     n_freqs, n_frames = N_FFT // 2 + 1, (n - 1) // HOP + 1
     per_ch = n * 4 + n_freqs * n_frames * 8
@@ -711,23 +723,26 @@ def run_e2e(eng, args, rank, world, window, x_dev, dev):
     ch = int(min(args.channels, max(1, (0.45 * avail / max(1, world)) // per_ch)))
     if args.e2e_channels:
         ch = min(ch, args.e2e_channels)
-    xh = th = None
+    xb = tb = None
     while ch >= 1:
-        try:
-            xh = torch.empty((ch, n), dtype=torch.float32, pin_memory=True)
-            th = torch.empty((ch, n_freqs, n_frames), dtype=torch.complex64, pin_memory=True)
+        xb, xp = _pinned_near(ch * n * 4, dev.index)
+        tb, tp = _pinned_near(ch * n_freqs * n_frames * 8, dev.index) if xb is not None else (None, None)
+        if tb is not None:
             break
-        except RuntimeError:
-            xh = th = None
-            ch //= 2
-    if xh is None:
+        if xb is not None:
+            load().ssq_host_free(xp)
+        xb = tb = None
+        ch //= 2
+    if tb is None:
         return {"value": None, "unit": "Msamples/s", "note": "could not pin host memory"}
+    xh = torch.from_numpy(xb.view(np.float32).reshape(ch, n))
+    th = tb.view(np.complex64).reshape(ch, n_freqs, n_frames)
     xh.copy_(x_dev[:ch])
     torch.cuda.synchronize()
     steps = max(1, min(args.steps, 3))
 
     def step():
-        eng.ssq_stft_host(xh.data_ptr(), ch, n, window, N_FFT, HOP, FS, th.data_ptr())
+        eng.ssq_stft_host(xp.value, ch, n, window, N_FFT, HOP, FS, tp.value)
 
     step()  # warm-up (allocates the device ring)
     if world > 1:
@@ -741,10 +756,39 @@ def run_e2e(eng, args, rank, world, window, x_dev, dev):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
     val = world * ch * n / (dt / steps) / 1e6
-    chk = float(th[0, :, :64].abs().sum().item())
+    chk = float(np.abs(th[0, :, :64]).sum())
+    d2h = ch * n_freqs * n_frames * 8
+    # ---- the ceiling: nothing but D2H copies into the same pinned buffer, every rank at the same time ----
+    scratch = torch.empty(min(d2h, 4 << 30), dtype=torch.uint8, device=dev)
+    cs = torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    c0 = time.perf_counter()
+    off = 0
+    while off < d2h:
+        m = min(scratch.numel(), d2h - off)
+        if load().ssq_memcpy_async(tp.value + off, scratch.data_ptr(), m, 2, cs.cuda_stream) != 0:
+            raise SystemExit("bench.py: ssq_memcpy_async failed")
+        off += m
+    cs.synchronize()
+    cdt = torch.tensor([time.perf_counter() - c0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cdt, op=dist.ReduceOp.MAX)
+    ceiling = world * d2h / float(cdt.item()) / 1e9
+    achieved = world * d2h / (dt / steps) / 1e9
+    node = __import__("ctypes").c_int(-2)
+    load().ssq_device_numa_node(dev.index, __import__("ctypes").byref(node))
+    del scratch
+    load().ssq_host_free(xp)
+    load().ssq_host_free(tp)
     return {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": int(ch * n * 4),
-            "d2h_bytes_per_step": int(ch * n_freqs * n_frames * 8), "channels_per_gpu": ch, "steps": steps,
+            "d2h_bytes_per_step": int(d2h), "channels_per_gpu": ch, "steps": steps,
             "ms_per_step": dt / steps * 1e3, "checksum": chk,
+            "d2h_gbs_achieved": achieved, "host_ceiling_gbs": ceiling, "frac_of_host_ceiling": achieved / ceiling,
+            "host_ceiling_note": "aggregate GB/s of plain cudaMemcpyAsync D2H copies of the same bytes into the same pinned "
+                                 "buffers, all ranks at once (no kernel, no H2D)",
+            "pinned_alloc": f"ssq_host_alloc_near (NUMA node of this rank's GPU: {node.value})",
             "note": "ssq_ssq_stft_host_f32: pinned host in/out, chunked H2D|kernel|D2H pipeline inside the call"}
 
 

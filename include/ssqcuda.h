@@ -278,6 +278,12 @@ ssq_status ssq_stream_push_f32(ssq_stream* s, const float* d_chunk, int64_t n_ne
 /* pinned host memory helpers for the host-buffer path */
 ssq_status ssq_host_alloc(void** p, size_t bytes);
 void ssq_host_free(void* p);
+/* plain cudaMemcpyAsync on a caller-provided cudaStream_t; kind 1 = host to device, 2 = device to host */
+ssq_status ssq_memcpy_async(void* dst, const void* src, size_t bytes, int kind, void* cuda_stream);
+/* NUMA node of the device's PCIe function (-1: unknown), and pinned host memory placed on it (the host gather of a
+ * multi-GPU box should not cross the socket interconnect); falls back to ssq_host_alloc when the node is unknown */
+ssq_status ssq_device_numa_node(int device, int* node);
+ssq_status ssq_host_alloc_near(void** p, size_t bytes, int device);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,9 @@
 #include "cwt_kernels.cuh"
 
 #include <algorithm>
+#include <ctype.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <thread>
 #include <stdlib.h>
 #include <new>
@@ -160,6 +163,57 @@ extern "C" ssq_status ssq_host_alloc(void** p, size_t bytes) {
 }
 extern "C" void ssq_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+// Plain asynchronous copy on a caller-provided stream (the measurement of the box's copy ceiling goes through the
+// same runtime instance as the library's own pipeline).
+extern "C" ssq_status ssq_memcpy_async(void* dst, const void* src, size_t bytes, int kind, void* cuda_stream) {
+  if (kind != 1 && kind != 2) return ssq_fail(nullptr, SSQ_EINVAL, "kind must be 1 (H2D) or 2 (D2H)");
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return ssq_fail(nullptr, SSQ_ECUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  return SSQ_OK;
+}
+
+// NUMA node the device's PCIe function hangs off (sysfs), -1 when the platform does not say.
+extern "C" ssq_status ssq_device_numa_node(int device, int* node) {
+  if (!node) return ssq_fail(nullptr, SSQ_EINVAL, "node is NULL");
+  *node = -1;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return ssq_fail(nullptr, SSQ_ECUDA, "cudaDeviceGetPCIBusId(%d) failed", device);
+  }
+  for (char* q = bus; *q; ++q) *q = (char)tolower((unsigned char)*q);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  if (FILE* f = fopen(path, "r")) {
+    int v = -1;
+    if (fscanf(f, "%d", &v) == 1) *node = v;
+    fclose(f);
+  }
+  return SSQ_OK;
+}
+
+// Pinned host memory placed on the device's NUMA node: the pages are allocated (and pinned) by cudaHostAlloc
+// while the calling thread's memory policy is MPOL_BIND to that node, then the policy is restored.  On an 8-GPU box
+// the host gather of Tx (44 GB per GPU and step on configs[1]) otherwise lands wherever the rank's thread happens to
+// run, and half of the copies cross the socket interconnect.  Falls back to a plain allocation when the node is
+// unknown or the policy call is refused.
+extern "C" ssq_status ssq_host_alloc_near(void** p, size_t bytes, int device) {
+  if (!p) return ssq_fail(nullptr, SSQ_EINVAL, "p is NULL");
+  int node = -1;
+  (void)ssq_device_numa_node(device, &node);
+  bool bound = false;
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    bound = syscall(SYS_set_mempolicy, 2 /* MPOL_BIND */, mask, (unsigned long)(8 * sizeof(mask))) == 0;
+  }
+  cudaSetDevice(device);
+  const ssq_status st = ssq_host_alloc(p, bytes);
+  if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+  return st;
 }
 
 // ===========================================================================
