@@ -247,6 +247,24 @@ ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_t channels,
 ssq_status ssq_issq_cwt_batch_f32(ssq_ctx* ctx, const float* d_Tx, int64_t channels, int64_t ns, int64_t n,
                                   int wavelet, const double* scales, float* d_x);
 
+/* ---- ridge extraction on a time-frequency map --------------------------------------------
+ * The reference crate declares rust/src/ridge/{mod,extraction}.rs and leaves them empty; the specification is
+ * upstream's forward/backward penalised ridge tracking, old/ssqueezepy/ridge_extraction.py:11-232 (sequential
+ * semantics).  Consumes Tx / Wx / Sx where it lies in HBM: only [n_time, n_ridges] indices have to leave the device.
+ * d_Tf: complex64 (is_f64 = 0: float arithmetic, eps = EPS32, as upstream does for complex64) or complex128
+ * [channels, n_freq, n_time]; scales: host float64 [n_freq] (the second argument of upstream's extract_ridges);
+ * transform: 0 'cwt' (penalty on log(scales)), 1 'stft' (on scales); d_ridge_idxs int32 [channels, n_time, n_ridges];
+ * d_ridge_f / d_ridge_e (optional, real type of Tf, same shape): scales / energies along the ridges;
+ * d_E_all (optional diagnostic, [channels, n_ridges, n_freq, n_time]): -log(energy / max + eps) of every ridge. */
+ssq_status ssq_extract_ridges_batch(ssq_ctx* ctx, const void* d_Tf, int is_f64, int64_t channels, int64_t n_freq,
+                                    int64_t n_time, const double* scales, double penalty, int n_ridges, int bw,
+                                    int transform, int32_t* d_ridge_idxs, void* d_ridge_f, void* d_ridge_e,
+                                    void* d_E_all);
+/* one map in HOST memory (complex64 or complex128 [n_freq, n_time]); outputs in host memory */
+ssq_status ssq_extract_ridges_host(ssq_ctx* ctx, const void* Tf, int is_f64, int64_t n_freq, int64_t n_time,
+                                   const double* scales, double penalty, int n_ridges, int bw, int transform,
+                                   int32_t* ridge_idxs, void* ridge_f, void* ridge_e, void* E_all);
+
 /* ---- batched path with HOST buffers (copies inside; synchronous) --------- */
 /* x: host fp32 [channels, n]; Tx: host complex64 [channels, n_freqs, n_frames] */
 ssq_status ssq_ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_t channels, int64_t n,

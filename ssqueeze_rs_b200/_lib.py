@@ -80,6 +80,10 @@ SIGNATURES = {
                                       c_int, c_int, c_dbl, c_u32, c_vp, c_vp]),
     "ssq_ssq_stft_host_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int, c_int,
                                       c_dbl, c_u32, c_vp]),
+    "ssq_extract_ridges_batch": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_dbl, c_int, c_int, c_int, c_vp,
+                                         c_vp, c_vp, c_vp]),
+    "ssq_extract_ridges_host": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_dbl, c_int, c_int, c_int, c_vp, c_vp,
+                                        c_vp, c_vp]),
     "ssq_stream_create": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int, c_int, c_dbl,
                                   C.POINTER(c_vp)]),
     "ssq_stream_destroy": (None, [c_vp]),

@@ -22,7 +22,7 @@ from ._lib import (FLAG_ADM_EXACT, FLAG_L2_NORM, FLAG_MODULATED, FLAG_NO_FLIPUD,
                    default_context, load, raise_status)
 
 __all__ = ["hello_from_bin", "stft", "ssq_stft", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt", "icwt", "issq_cwt",
-           "adm_ssq"]
+           "adm_ssq", "extract_ridges"]
 
 
 def _f64_1d(a, name):
@@ -318,3 +318,35 @@ def issq_cwt(Tx, wavelet="gmw", scales=None, cc=None, cw=None):
     st = load().ssq_issq_cwt_f64(ctx.handle, _ptr(Tx), ns, n, wid, _ptr(sc), _ptr(x))
     raise_status(st, ctx.handle)
     return x
+
+
+def extract_ridges(Tf, scales, penalty=2.0, n_ridges=1, bw=15, transform="cwt", get_params=False, parallel=True, *,
+                   return_E=False):
+    """Forward/backward penalised ridge tracking on a time-frequency map.  The reference crate
+    declares `ridge::extraction` and leaves it empty (rust/src/ridge/{mod,extraction}.rs); signature, semantics and
+    return values are upstream's `extract_ridges` (old/ssqueezepy/ridge_extraction.py:11-150): ridge_idxs int
+    [n_time, n_ridges] (and ridge_f, ridge_e with `get_params`).  Tf: complex128 (float64 arithmetic, eps = EPS64) or
+    complex64 (float32, EPS32) [n_freq, n_time]; `parallel` is accepted and ignored (the result is that of upstream's
+    sequential code).  `return_E=True` appends the diagnostic E = -log(energy / max + eps) of every ridge."""
+    if not isinstance(Tf, np.ndarray) or Tf.ndim != 2 or Tf.dtype not in (np.complex128, np.complex64):
+        raise TypeError("argument 'Tf': expected a 2-D numpy.ndarray of complex128 or complex64")
+    Tf = np.ascontiguousarray(Tf)
+    is64 = Tf.dtype == np.complex128
+    rdt = np.float64 if is64 else np.float32
+    sc = np.ascontiguousarray(np.asarray(scales, dtype=np.float64).reshape(-1))
+    nf, nt = Tf.shape
+    if len(sc) != nf:
+        raise ValueError(f"scales has {len(sc)} entries, Tf has {nf} rows")
+    tr = 0 if _str(transform, "transform") == "cwt" else 1
+    idx = np.empty((nt, int(n_ridges)), dtype=np.int32)
+    rf = np.empty((nt, int(n_ridges)), dtype=rdt) if get_params else None
+    re_ = np.empty((nt, int(n_ridges)), dtype=rdt) if get_params else None
+    E = np.empty((int(n_ridges), nf, nt), dtype=rdt) if return_E else None
+    ctx = default_context()
+    st = load().ssq_extract_ridges_host(ctx.handle, _ptr(Tf), 1 if is64 else 0, nf, nt, _ptr(sc), float(penalty),
+                                        int(n_ridges), int(bw), tr, _ptr(idx), _ptr(rf), _ptr(re_), _ptr(E))
+    raise_status(st, ctx.handle)
+    out = (idx.astype(int), rf, re_) if get_params else idx.astype(int)
+    if return_E:
+        return (out + (E,)) if get_params else (out, E)
+    return out

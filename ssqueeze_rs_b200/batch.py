@@ -226,6 +226,28 @@ class Engine:
         raise_status(st, self.ctx.handle)
         return x
 
+    def extract_ridges(self, Tf, scales, penalty=2.0, n_ridges=1, bw=15, transform="cwt", get_params=False):
+        """Tf: complex64 CUDA [channels, n_freq, n_time] (e.g. the Tx `ssq_stft` / `ssq_cwt` just wrote) -> ridge indices
+        int32 [channels, n_time, n_ridges] (and ridge_f, ridge_e float32 with get_params).  The map never leaves HBM."""
+        import torch
+        assert Tf.is_cuda and Tf.dim() == 3 and Tf.is_contiguous() and Tf.dtype in (torch.complex64, torch.complex128)
+        ch, nf, nt = Tf.shape
+        is64 = Tf.dtype == torch.complex128
+        sc = np.ascontiguousarray(np.asarray(scales, dtype=np.float64).reshape(-1))
+        assert len(sc) == nf
+        idx = torch.empty((ch, nt, n_ridges), dtype=torch.int32, device=Tf.device)
+        rdt = torch.float64 if is64 else torch.float32
+        rf = torch.empty((ch, nt, n_ridges), dtype=rdt, device=Tf.device) if get_params else None
+        re_ = torch.empty((ch, nt, n_ridges), dtype=rdt, device=Tf.device) if get_params else None
+        self._bind_stream()
+        st = load().ssq_extract_ridges_batch(self.ctx.handle, C.c_void_p(Tf.data_ptr()), 1 if is64 else 0, ch, nf, nt,
+                                             C.c_void_p(sc.ctypes.data), float(penalty), int(n_ridges), int(bw),
+                                             0 if transform == "cwt" else 1, C.c_void_p(idx.data_ptr()),
+                                             C.c_void_p(rf.data_ptr() if get_params else 0),
+                                             C.c_void_p(re_.data_ptr() if get_params else 0), C.c_void_p(0))
+        raise_status(st, self.ctx.handle)
+        return (idx, rf, re_) if get_params else idx
+
     def default_scales(self, n, nv=32, simd=False):
         ns = load().ssq_cwt_default_scales(int(n), int(nv), int(simd), C.c_void_p(0))
         sc = np.empty(ns, dtype=np.float64)

@@ -12,6 +12,7 @@
 #include "istft_r1024.cuh"
 #include "istft_r256.cuh"
 #include "cwt_kernels.cuh"
+#include "ridge_kernels.cuh"
 
 #include <algorithm>
 #include <ctype.h>
@@ -114,6 +115,8 @@ extern "C" void ssq_ctx_destroy(ssq_ctx* ctx) {
                     &ctx->ws_fft1, &ctx->ws_misc, &ctx->tab, &ctx->cwt_tw, &ctx->cwt_scales};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  for (DevBuf& b : ctx->ws_ridge)
+    if (b.p) cudaFree(b.p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 2; ++i) {
@@ -1196,3 +1199,4 @@ extern "C" ssq_status ssq_stream_push_f32(ssq_stream* s, const float* d_chunk, i
 }
 
 #include "cwt_host.inl"
+#include "ridge_host.inl"

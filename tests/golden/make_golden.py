@@ -30,6 +30,10 @@
   rounding for gmw; for morlet only where psi-hat is negligible at the Nyquist bin (the Rust grid
   keeps +pi there, `wavelets/base.rs:18-33`, upstream -pi) -- rows `morlet_rows_ok`.
 
+* `upstream_ridges.npz` -- upstream `extract_ridges(..., parallel=False, get_params=True)`
+  (`ridge_extraction.py:11-232`; the sequential JIT code: the parallel one races on the ridge index) on a
+  two-chirp CWT-like map and an STFT-like map, float64 and float32, 1-3 ridges: pins oracle/ridge_oracle.py.
+
 Neither the GPU tests nor bench.py read /root/reference; they read these files.
 """
 import os
@@ -168,7 +172,44 @@ def upstream_cwt():
     return out
 
 
+def upstream_ridges():
+    from ssqueezepy.ridge_extraction import extract_ridges
+    rng = np.random.default_rng(20261019)
+    out = {}
+    cases = []
+    T = 300
+    t = np.arange(T)
+    for ci, (F, transform, n_ridges, bw, penalty, cdt) in enumerate([
+            (48, "cwt", 2, 4, 2.0, np.complex128), (48, "cwt", 1, 15, 20.0, np.complex64),
+            (65, "stft", 3, 3, 0.5, np.complex128), (65, "stft", 2, 2, 5.0, np.complex64)]):
+        f = np.arange(F)[:, None]
+        c1 = 8 + 25 * t / T
+        c2 = F - 10 - 12 * np.sin(2 * np.pi * t / T)
+        Tf = (np.exp(-0.5 * ((f - c1[None]) / 1.2) ** 2) + 0.6 * np.exp(-0.5 * ((f - c2[None]) / 1.5) ** 2)
+              + 0.05 * rng.standard_normal((F, T))) * np.exp(2j * np.pi * rng.random((F, T)))
+        Tf = Tf.astype(cdt)
+        scales = (2.0 ** np.linspace(1, 6, F)) if transform == "cwt" else np.linspace(0, 0.5, F)
+        if transform == "stft":
+            scales = scales + 1e-3  # log() is not taken for 'stft'; keep a generic grid
+        idx, rf, re_ = extract_ridges(Tf, scales, penalty=penalty, n_ridges=n_ridges, bw=bw, transform=transform,
+                                      get_params=True, parallel=False)
+        p = f"r{ci}_"
+        out[p + "Tf"] = Tf
+        out[p + "scales"] = scales
+        out[p + "idx"] = idx
+        out[p + "ridge_f"] = rf
+        out[p + "ridge_e"] = re_
+        cases.append((F, n_ridges, bw, penalty, 0 if transform == "cwt" else 1))
+    out["cases"] = np.array(cases, dtype=np.float64)
+    return out
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ridges":  # regenerate one file only
+        np.savez_compressed(os.path.join(HERE, "upstream_ridges.npz"), **upstream_ridges())
+        print("upstream_ridges.npz", os.path.getsize(os.path.join(HERE, "upstream_ridges.npz")), "bytes")
+        sys.exit(0)
+    np.savez_compressed(os.path.join(HERE, "upstream_ridges.npz"), **upstream_ridges())
     np.savez_compressed(os.path.join(HERE, "upstream_components.npz"), **upstream_components())
     np.savez_compressed(os.path.join(HERE, "upstream_even512.npz"), **upstream_even512())
     np.savez_compressed(os.path.join(HERE, "upstream_cwt.npz"), **upstream_cwt())
