@@ -285,6 +285,8 @@ def _finish_record(r, dev, world):
                         "note": "per GPU; whole step (all kernels of the call), not one kernel"},
            "kernel": kernel}
     rec.update(extra)
+    if rec.get("scaling") == "weak":
+        rec["roofline"]["note"] = "per GPU; wall clock of the whole host-to-host step"
     return rec
 
 
@@ -440,12 +442,54 @@ def side_c3_ssq_cwt(torch, eng, dev, rank, world, stream, g, cpu, scale=1.0):
     return rec
 
 
+def side_ridges_e2e(torch, eng, dev, rank, world, stream, g, cpu, scale=1.0):
+    """The consumer that stays on the device: pinned host x -> H2D -> ssq_stft (configs[1] geometry)
+    -> ridge extraction on Tx where it lies in HBM -> D2H of the ridge indices only (0.2 % of Tx's bytes).  Timed end
+    to end like `e2e` (host buffers, copies inside the timed region); every rank runs its own batch (weak scaling)."""
+    ch, n = max(1, int(CHANNELS * scale)), SAMPLES
+    win = np.hanning(N_FFT)
+    nfq, nfr = N_FFT // 2 + 1, (n - 1) // HOP + 1
+    xh = torch.empty((ch, n), dtype=torch.float32, pin_memory=True)
+    xh.copy_(make_neural(torch, ch, n, FS, dev, 0x5351 + rank))
+    rh = torch.empty((ch, nfr, 1), dtype=torch.int32, pin_memory=True)
+    xd = torch.empty((ch, n), dtype=torch.float32, device=dev)
+    Tx = torch.empty((ch, nfq, nfr), dtype=torch.complex64, device=dev)
+    sf = np.arange(nfq) * 0.5 / (nfq - 1) + 1e-9  # normalised frequencies (upstream's `scales` for an STFT map)
+    torch.cuda.synchronize()
+
+    def step():
+        with torch.cuda.stream(stream):
+            xd.copy_(xh, non_blocking=True)
+            eng.ssq_stft(xd, win, N_FFT, HOP, FS, out=Tx, modulated=True)
+            idx = eng.extract_ridges(Tx, sf, penalty=2.0, n_ridges=1, bw=4, transform="stft")
+            rh.copy_(idx, non_blocking=True)
+        stream.synchronize()
+
+    step()
+    t0 = time.perf_counter()
+    steps = 2
+    for _ in range(steps):
+        step()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    med = float(np.median(rh[0, :, 0].numpy()))
+    rec = _record("ssq_stft+extract_ridges (e2e)", float(ch) * n, ms, algorithmic_bytes(ch, n), dev, world,
+                  f"configs[1] geometry, {ch}ch x {n} per GPU: host x -> ssq_stft(modulated) -> extract_ridges(penalty 2, 1 ridge) "
+                  f"on device -> host ridge indices", "ssq_stft512_h32r_kernel<ssq> + ridge_forward_kernel",
+                  {"e2e": {"h2d_bytes_per_step": int(ch * n * 4), "d2h_bytes_per_step": int(ch * nfr * 4),
+                           "note": "wall clock around the public Engine calls, pinned host in/out"},
+                   "scaling": "weak", "median_ridge_bin_channel0": med})
+    del xd, Tx, xh, rh
+    torch.cuda.empty_cache()
+    return rec
+
+
 def side_configs(torch, eng, dev, rank, world, stream, cpu, scale=1.0):
     g = torch.Generator(device=dev)
     g.manual_seed(0x5351 + rank)
     out = {}
     from ssqueeze_rs_b200.dist import max_over_ranks
-    for key, fn in (("c5", side_c5), ("c4_istft", side_c4_istft), ("c3_ssq_cwt", side_c3_ssq_cwt)):
+    for key, fn in (("c5", side_c5), ("c4_istft", side_c4_istft), ("c3_ssq_cwt", side_c3_ssq_cwt),
+                    ("c2_ridges_e2e", side_ridges_e2e)):
         r, err = None, None
         try:
             r = fn(torch, eng, dev, rank, world, stream, g, cpu, scale)

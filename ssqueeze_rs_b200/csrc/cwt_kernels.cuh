@@ -122,7 +122,7 @@ struct FftPass {
   int tw_s;
   int64_t row0;       // global row index of row 0 of this launch
   // ---- load functor -------------------------------------------------------------
-  int load_mode;      // 0 plain, 1 padded real signal, 2 x-hat * psi-hat
+  int load_mode;      // 0 plain, 1 padded real signal, 2 x-hat * psi-hat, 3 windowed STFT frame, 4 plain * mul[idx], 5 istft column
   const float* x;     // [channels, x_stride] (mode 1)
   int64_t x_stride, n;
   int padtype;
@@ -132,6 +132,18 @@ struct FftPass {
   int wavelet;
   float inv_dt;
   int up_shift;       // mode 2: 7 * (number of leading passes skipped as broadcasts), see cwt_host.inl
+  // mode 3 (STFT family through the row passes: n_fft > 4096 or not a power of two; stft_rows.inl): row r of the
+  // launch is frame fr_first + r % fr_count of channel r / fr_count; element n < fr_nfft is
+  // x_pad[frame * hop + n] * (win[n] + i dwin[n]) (* chirp[n] for Bluestein), the rest of the row is zero
+  const float2* fr_wpair;  // [n_fft] (win, dwin * s)
+  const float2* fr_chirp;  // [n_fft] exp(-i pi n^2 / n_fft) or NULL
+  int fr_nfft, fr_hop, fr_left, fr_count;
+  int64_t fr_first, fr_origin;
+  // mode 5 (istft through the row passes): element n of the row is conj(Zfull[n]) (* chirp[n]), Zfull the Hermitian
+  // extension of column fr_first + r % fr_count of in = Sx[channel][n_fft/2+1][fr_ld]
+  int64_t fr_ld;
+  // mode 4: in[row][idx] * mul[idx] (Bluestein: spectrum of the chirp filter, 1/M folded in)
+  const float2* mul;
   // ---- store functor ------------------------------------------------------------
   int store_mode;     // 0 plain, 1 final: scaled, unpadded rows to outW / outD, 2: fused ssq_cwt epilogue
   float2* outW;       // [channels, ns, out_cols]
@@ -196,6 +208,26 @@ __device__ __forceinline__ float2 pass_load(const FftPass& P, int row, int64_t i
   if (P.load_mode == 0) return P.in[(size_t)row * L + idx];
   const int64_t g = P.row0 + row;
   if (P.load_mode == 1) return make_float2(cwt_sample(P, (int)g, idx, L), 0.f);
+  if (P.load_mode == 4) return cmulf(P.in[(size_t)row * L + idx], __ldg(P.mul + idx));
+  if (P.load_mode == 5) {
+    if (idx >= P.fr_nfft) return make_float2(0.f, 0.f);
+    const int64_t ch = g / P.fr_count, frame = P.fr_first + (g - ch * P.fr_count);
+    const int nfq = P.fr_nfft / 2 + 1;
+    const int k = idx < nfq ? (int)idx : P.fr_nfft - (int)idx;
+    float2 v = P.in[((size_t)ch * nfq + k) * P.fr_ld + frame];
+    if (idx < nfq) v.y = -v.y;
+    if (P.fr_chirp) v = cmulf(v, __ldg(P.fr_chirp + idx));
+    return v;
+  }
+  if (P.load_mode == 3) {
+    if (idx >= P.fr_nfft) return make_float2(0.f, 0.f);
+    const int64_t ch = g / P.fr_count, frame = P.fr_first + (g - ch * P.fr_count);
+    const float xv = stft_sample(P.x + (size_t)ch * P.x_stride, P.n, frame * P.fr_hop + idx, P.fr_left, P.padtype, P.fr_origin);
+    const float2 w = __ldg(P.fr_wpair + idx);
+    float2 v = make_float2(xv * w.x, xv * w.y);
+    if (P.fr_chirp) v = cmulf(v, __ldg(P.fr_chirp + idx));
+    return v;
+  }
   // mode 2: row g -> (channel, scale, which)
   const int which = (int)(g % P.nd);
   const int64_t cs = g / P.nd;

@@ -12,11 +12,42 @@ namespace ssqhost {
 
 typedef std::complex<double> cd;
 
-// plain DFT / FFT in double: radix-2 for powers of two, O(n^2) otherwise
+// exp(-i pi m^2 / n) with the phase reduced in integers (m^2 mod 2n): exact argument for any m
+inline cd chirp(int64_t m, int64_t n) {
+  const double PI = 3.14159265358979323846;
+  const int64_t r = (int64_t)(((unsigned __int128)m * (unsigned __int128)m) % (unsigned __int128)(2 * n));
+  const double ang = -PI * (double)r / (double)n;
+  return cd(std::cos(ang), std::sin(ang));
+}
+
+// plain DFT / FFT in double: radix-2 for powers of two, Bluestein on top of it otherwise (tiny n: direct sum)
 inline void dft(std::vector<cd>& a, bool inverse) {
   const size_t n = a.size();
   if (n <= 1) return;
   const double PI = 3.14159265358979323846;
+  if ((n & (n - 1)) != 0 && n > 32) {
+    // X[k] = c[k] sum_j (a[j] c[j]) conj(c[k - j]), c[m] = exp(-i pi m^2 / n) (conjugated for the inverse)
+    size_t M = 1;
+    while (M < 2 * n - 1) M <<= 1;
+    std::vector<cd> u(M, cd(0.0, 0.0)), h(M, cd(0.0, 0.0));
+    for (size_t j = 0; j < n; ++j) {
+      cd c = chirp((int64_t)j, (int64_t)n);
+      if (inverse) c = std::conj(c);
+      u[j] = a[j] * c;
+      h[j] = std::conj(c);
+      if (j) h[M - j] = std::conj(c);
+    }
+    dft(u, false);
+    dft(h, false);
+    for (size_t i = 0; i < M; ++i) u[i] *= h[i];
+    dft(u, true);
+    for (size_t k = 0; k < n; ++k) {
+      cd c = chirp((int64_t)k, (int64_t)n);
+      if (inverse) c = std::conj(c);
+      a[k] = u[k] * c / (double)M;
+    }
+    return;
+  }
   if ((n & (n - 1)) == 0) {
     for (size_t i = 1, j = 0; i < n; ++i) {
       size_t bit = n >> 1;

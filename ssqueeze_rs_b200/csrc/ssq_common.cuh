@@ -32,6 +32,8 @@ struct ssq_ctx {
   std::string err;
   // workspaces
   DevBuf ws_in, ws_out, ws_aux0, ws_aux1, ws_aux2, ws_fft0, ws_fft1, ws_misc;
+  DevBuf rows_tab;     // Bluestein chirp + filter spectrum of the rows path (stft_rows.inl), cached by n_fft
+  int rows_n = -1;
   DevBuf ws_ridge[5];  // ridge extraction: energy, E, P, work indices, scale table
   // STFT table cache (window / diff-window / twiddles on device)
   DevBuf tab;

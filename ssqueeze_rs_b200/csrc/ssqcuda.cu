@@ -117,6 +117,7 @@ extern "C" void ssq_ctx_destroy(ssq_ctx* ctx) {
     if (b->p) cudaFree(b->p);
   for (DevBuf& b : ctx->ws_ridge)
     if (b.p) cudaFree(b.p);
+  if (ctx->rows_tab.p) cudaFree(ctx->rows_tab.p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 2; ++i) {
@@ -392,6 +393,9 @@ struct StftCall {
   int64_t x_origin = 0;  // global sample index of d_x[.][0]
 };
 
+static ssq_status stft_rows_run(ssq_ctx* ctx, StftParams P, bool* done);  // stft_rows.inl
+static ssq_status istft_rows_run(ssq_ctx* ctx, IstftParams P, bool* done);
+
 static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const int N = c.n_fft;
@@ -460,6 +464,7 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
       if (st != SSQ_OK) return st;
     }
   }
+  if (!done) SSQ_TRY(stft_rows_run(ctx, P, &done));  // n_fft > 4096, or not a power of two: batched row FFTs
   if (!done) {
     TilePlan tp;
     SSQ_TRY(plan_generic_tiles(ctx, N, n_freqs, n_frames, (int)c.channels, &tp, &P.tiles_per_channel,
@@ -694,6 +699,20 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
   P.wa = T.wa;
   P.tw = T.tw;
   P.xacc = (float*)ctx->ws_misc.p;
+  {  // n_fft > 4096 or not a power of two: batched row FFTs
+    bool rows_done = false;
+    SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    SSQ_TRY(istft_rows_run(ctx, P, &rows_done));
+    if (rows_done) {
+      SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+      ctx->ev_valid = true;
+      dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
+      istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
+                                                        (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+      SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
+      return SSQ_OK;
+    }
+  }
   TilePlan tp;
   SSQ_TRY(plan_generic_tiles(ctx, n_fft, (int)n_freqs, P.n_use, (int)channels, &tp, &P.tiles_per_channel,
                              &P.total_tiles));
@@ -1199,4 +1218,5 @@ extern "C" ssq_status ssq_stream_push_f32(ssq_stream* s, const float* d_chunk, i
 }
 
 #include "cwt_host.inl"
+#include "stft_rows.inl"
 #include "ridge_host.inl"

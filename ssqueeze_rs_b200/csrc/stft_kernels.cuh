@@ -50,6 +50,13 @@ struct StftParams {
   int F;                // frames per tile
   int acc_stride;       // odd >= n_freqs
   int64_t tiles_per_channel, total_tiles;
+  // rows mode of the generic kernel (stft_rows.inl): the frame spectra were computed by the batched row passes;
+  // Z of local frame f of channel ch is zrows[(ch * n_frames + f) * zld + k] (times zmul[k] when given: Bluestein)
+  const float2* zrows;
+  const float2* zmul;
+  int64_t zld;
+  int64_t out_ld;       // row stride of `out` / aux (0: n_frames)
+  int64_t fbase;        // istft rows mode: global index of local frame 0 (rows are indexed (ch * n_use + f))
 };
 
 // Bin index of the reference's arg-min (ssq_stft.rs:280-289) from the bin-unit
@@ -66,7 +73,7 @@ __device__ __forceinline__ int ssq_bin_from(float binf, int n_freqs) {
 // (c, d) = 2 Sx, (a, b) = 2 V as the kernel used them; base = (ch * n_freqs) * n_frames + local frame.
 __device__ __forceinline__ void ssq_dbg_emit(const StftParams& P, size_t base, int k, float c, float d, float a,
                                              float b, float binf, bool gated, int kb) {
-  const size_t o = base + (size_t)k * P.n_frames;
+  const size_t o = base + (size_t)k * (P.out_ld ? P.out_ld : P.n_frames);
   if (P.aux_Sx) P.aux_Sx[o] = make_float2(0.5f * c, 0.5f * d);
   if (P.aux_dSx) P.aux_dSx[o] = make_float2(a * P.dsx_scale, b * P.dsx_scale);
   if (P.aux_w) P.aux_w[o] = gated ? __int_as_float(0x7f800000) : binf * P.dw_f;
@@ -152,7 +159,14 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
   float2* twid = acc + (size_t)P.F * P.acc_stride + (size_t)nw * 2 * N;
   // per-warp destination-bin tags (n_freqs bytes, rounded up to 8) behind the twiddles
   unsigned char* tag = reinterpret_cast<unsigned char*>(twid + N) + (size_t)warp * ((P.n_freqs + 7) & ~7);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) twid[i] = P.tw[i];
+  const bool rows = P.zrows != nullptr;  // spectra come from the row passes: no per-warp work buffers, no twiddles
+  if (rows) {
+    twid = nullptr;
+    tag = reinterpret_cast<unsigned char*>(acc + (size_t)P.F * P.acc_stride) + (size_t)warp * ((P.n_freqs + 7) & ~7);
+  } else {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) twid[i] = P.tw[i];
+  }
+  const int64_t old = P.out_ld ? P.out_ld : P.n_frames;
 
   for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const int ch = (int)(tile / P.tiles_per_channel);
@@ -165,14 +179,19 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
     for (int fl = warp; fl < nf; fl += nw) {
       const int64_t frame = f0 + fl;
       const int64_t start = (P.frame0 + frame) * P.hop;
-      float2* A = work;
-      float2* B = work + N;
-      for (int n = lane; n < N; n += 32) {
-        float xv = stft_sample(xc, P.n, start + n, P.left, P.padtype, P.x_origin);
-        A[n] = make_float2(xv * P.win[n], xv * P.dwin[n]);
+      const float2* Z;
+      if (rows) {
+        Z = P.zrows + ((size_t)ch * P.n_frames + frame) * P.zld;
+      } else {
+        float2* A = work;
+        float2* B = work + N;
+        for (int n = lane; n < N; n += 32) {
+          float xv = stft_sample(xc, P.n, start + n, P.left, P.padtype, P.x_origin);
+          A[n] = make_float2(xv * P.win[n], xv * P.dwin[n]);
+        }
+        __syncwarp();
+        Z = warp_fft_generic(A, B, twid, N, P.log2n, P.is_pow2, lane);
       }
-      __syncwarp();
-      float2* Z = warp_fft_generic(A, B, twid, N, P.log2n, P.is_pow2, lane);
 
       // split + phase transform + reassignment.  Lane owns the S consecutive bins lane*S .. lane*S+S-1
       // (S odd: conflict-free strided reads of Z), so the 32 sources of a step are S bins apart and
@@ -186,14 +205,18 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
         int kb = -1;
         float vre = 0.f, vim = 0.f;
         if (valid) {
-          const float2 zk = Z[k];
-          const float2 zn = Z[k == 0 ? 0 : N - k];
+          float2 zk = Z[k];
+          float2 zn = Z[k == 0 ? 0 : N - k];
+          if (rows && P.zmul) {
+            zk = cmulf(zk, __ldg(P.zmul + k));
+            zn = cmulf(zn, __ldg(P.zmul + (k == 0 ? 0 : N - k)));
+          }
           float c = zk.x + zn.x, d = zk.y - zn.y;  // 2*Sx
           float a = zk.y + zn.y, b = zn.x - zk.x;  // 2*V
           if (P.modulated) {
             // multiply by exp(+2 pi i k (N/2)/N) = conj(tw[(k*(N/2)) mod N])
             const int m = (int)(((int64_t)k * (N / 2)) % N);
-            const float2 t = twid[m];
+            const float2 t = rows ? __ldg(P.tw + m) : twid[m];
             float2 s2 = make_float2(c * t.x + d * t.y, d * t.x - c * t.y);
             float2 v2 = make_float2(a * t.x + b * t.y, b * t.x - a * t.y);
             c = s2.x; d = s2.y; a = v2.x; b = v2.y;
@@ -202,7 +225,7 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
           const bool gated = den < P.gate2;  // |Sx| < gamma (ssq_stft.rs:23)
           const float binf = fabsf((float)k - (b * c - a * d) / den * P.cphase);
           if (P.mode == 0 && (P.aux_Sx || P.aux_dSx || P.aux_w || P.aux_kb))
-            ssq_dbg_emit(P, (size_t)ch * P.n_freqs * P.n_frames + frame, k, c, d, a, b, binf, gated,
+            ssq_dbg_emit(P, (size_t)ch * P.n_freqs * old + frame, k, c, d, a, b, binf, gated,
                          ssq_bin_from(binf, P.n_freqs));
           if (P.mode == 1) {
             col[k] = make_float2(0.5f * c, 0.5f * d);
@@ -232,11 +255,11 @@ __global__ void __launch_bounds__(256) stft_generic_kernel(const StftParams P) {
     }
     __syncthreads();
     // coalesced store: consecutive threads -> consecutive frames of one row
-    float2* outc = P.out + (size_t)ch * P.n_freqs * P.n_frames + f0;
+    float2* outc = P.out + (size_t)ch * P.n_freqs * old + f0;
     const int total = P.n_freqs * P.F;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
       const int k = i / P.F, f = i - k * P.F;
-      if (f < nf) outc[(size_t)k * P.n_frames + f] = acc[(size_t)f * P.acc_stride + k];
+      if (f < nf) outc[(size_t)k * old + f] = acc[(size_t)f * P.acc_stride + k];
     }
     __syncthreads();
   }
@@ -285,6 +308,13 @@ struct IstftParams {
   float* xacc;          // [channels, L], zero-initialised
   int F, acc_stride;
   int64_t tiles_per_channel, total_tiles;
+  // rows mode of the generic kernel (stft_rows.inl): the frame spectra were computed by the batched row passes;
+  // Z of local frame f of channel ch is zrows[(ch * n_frames + f) * zld + k] (times zmul[k] when given: Bluestein)
+  const float2* zrows;
+  const float2* zmul;
+  int64_t zld;
+  int64_t out_ld;       // row stride of `out` / aux (0: n_frames)
+  int64_t fbase;        // istft rows mode: global index of local frame 0 (rows are indexed (ch * n_use + f))
 };
 
 __global__ void __launch_bounds__(256) istft_ola_kernel(const IstftParams P) {
@@ -295,12 +325,25 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const IstftParams P) {
   float2* S = smem;  // [F][acc_stride]
   float2* work = S + (size_t)P.F * P.acc_stride + (size_t)warp * 2 * N;
   float2* twid = S + (size_t)P.F * P.acc_stride + (size_t)nw * 2 * N;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) twid[i] = P.tw[i];
+  const bool rows = P.zrows != nullptr;
+  if (!rows)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) twid[i] = P.tw[i];
 
   for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const int ch = (int)(tile / P.tiles_per_channel);
     const int64_t f0 = (tile % P.tiles_per_channel) * P.F;
     const int nf = (int)min((int64_t)P.F, P.n_use - f0);
+    if (rows) {
+      for (int fl = warp; fl < nf; fl += nw) {
+        const float2* Z = P.zrows + ((size_t)ch * P.n_use + f0 + fl) * P.zld;
+        float* rr = reinterpret_cast<float*>(S + (size_t)fl * P.acc_stride);
+        for (int n = lane; n < N; n += 32) {
+          float2 z = Z[n];
+          if (P.zmul) z = cmulf(z, __ldg(P.zmul + n));
+          rr[n] = z.x * P.wa[n];
+        }
+      }
+    } else {
     const float2* in = P.Sx + (size_t)ch * P.n_freqs * P.n_frames + f0;
     const int total = P.n_freqs * P.F;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -323,9 +366,10 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const IstftParams P) {
       for (int n = lane; n < N; n += 32) rr[n] = Z[n].x * P.wa[n];
       __syncwarp();
     }
+    }
     __syncthreads();
     const int span = (nf - 1) * P.hop + N;
-    float* xo = P.xacc + (size_t)ch * P.L + f0 * P.hop;
+    float* xo = P.xacc + (size_t)ch * P.L + (P.fbase + f0) * P.hop;
     for (int p = threadIdx.x; p < span; p += blockDim.x) {
       int fhi = min(nf - 1, p / P.hop);
       int flo = (p - N + P.hop) / P.hop;  // ceil((p-N+1)/hop) for p-N+1 > 0

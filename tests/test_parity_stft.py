@@ -105,6 +105,37 @@ def test_ssq_stft_non_pow2(n_fft, hop, N):
     check_ssq(x, win, n_fft, hop, fs=1.0)
 
 
+@pytest.mark.parametrize("n_fft,hop,N", [(500, 125, 6000), (1000, 100, 5000), (3000, 750, 20000), (8192, 2048, 40000),
+                                         (6000, 1500, 30000), (16384, 8192, 50000), (4097, 1000, 9000)])
+def test_ssq_stft_any_length_rows_path(n_fft, hop, N):
+    """The reference takes any n_fft (rustfft, ssq_stft.rs:92,198-199): lengths above 4096 and lengths that are not
+    powers of two run through the batched row FFT (Bluestein for the latter), then the same split / phase transform /
+    reassignment; every bin classified against the oracle, stft and the istft of the result as well."""
+    rs = _rs()
+    from ssqueeze_rs_b200 import _lib
+    rng = np.random.default_rng(n_fft)
+    x = rng.standard_normal(N) * 3.0
+    win = np.hanning(n_fft + 2)[1:-1].copy()
+    rep = check_ssq(x, win, n_fft, hop, fs=1000.0, expect_kernel="rows")
+    assert rep["unexplained"] == 0
+    check_ssq(x, win, n_fft, hop, fs=1000.0, expect_kernel="rows", padtype="zero", squeezing="lebesgue")
+    check_ssq(x, win, n_fft, hop, fs=1000.0, expect_kernel="rows", modulated=True)
+    Sx, _ = rs.stft(x, n_fft, hop, win, "reflect")
+    assert "rows" in _lib.default_context().last_kernel_name()
+    So, _ = O.stft(x, n_fft, hop, win, "reflect")
+    assert rel(Sx, So) < RTOL, rel(Sx, So)
+    # the inverse through the same row passes: against the oracle on a modified spectrum, and the round trip
+    Sm = So * (1 + 0.05 * rng.standard_normal(So.shape))
+    for wexp in (1, 0):
+        xr = rs.istft(Sm, win, n_fft=n_fft, hop_len=hop, N=N, win_exp=wexp)
+        assert "rows" in _lib.default_context().last_kernel_name()
+        xo = O.istft(Sm, win, n_fft=n_fft, hop_len=hop, N=N, win_exp=wexp)
+        assert np.abs(xr - xo).max() < RTOL * max(np.abs(xo).max(), 1e-30), (n_fft, wexp)
+    if hop * 2 <= n_fft:
+        xb = rs.istft(Sx, win, n_fft=n_fft, hop_len=hop, N=N)
+        assert np.abs(xb - x).max() < 1e-4 * np.abs(x).max()
+
+
 def test_ssq_stft_vs_upstream_golden():
     z = np.load(os.path.join(G, "upstream_odd.npz"))
     rs = _rs()
