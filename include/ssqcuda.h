@@ -247,6 +247,20 @@ ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_t channels,
 ssq_status ssq_issq_cwt_batch_f32(ssq_ctx* ctx, const float* d_Tx, int64_t channels, int64_t ns, int64_t n,
                                   int wavelet, const double* scales, float* d_x);
 
+/* ---- wavelet generators --------------------------------------------------------------
+ * The functions src/ssqueeze/_rs.pyi:91-132 declares: `morlet`, `morlet_freq`, `morlet_time` (rust/src/wavelets/
+ * morlet.rs:59-146), `gmw`, `gmw_freq`, `gmw_time`, `gmw_center_frequency` (gmw.rs:226-358).  Host arithmetic in
+ * double (they are O(n)); no device is needed.  kind: 0 = psi-hat at the given w[n]; 1 = psi-hat on xifn(scale, n)
+ * (base.rs:18-33; `w` unused); 2 = the time-domain wavelet (psi-hat (-1)^i, Nyquist bin halved for even n, inverse
+ * DFT / n).  out: complex128 [n]. */
+ssq_status ssq_wavelet_morlet(int kind, const double* w, int64_t n, double scale, double mu, double* out);
+/* norm_bandpass: norm.to_lowercase() == "bandpass" (anything else is the L2 / "energy" normalisation, gmw.rs:44-52);
+ * with kind 0 the argument checks of `gmw` apply (SSQ_EINVAL: gamma <= 0, beta < 0, order < 0; gmw.rs:238-246) */
+ssq_status ssq_wavelet_gmw(int kind, const double* w, int64_t n, double scale, double gamma, double beta,
+                           int norm_bandpass, int order, double* out);
+/* kind: 0 "peak" = (beta/gamma)^(1/gamma), 1 "energy" (gmw.rs:331-357) */
+ssq_status ssq_wavelet_gmw_center_frequency(double gamma, double beta, int kind, double* out);
+
 /* ---- ridge extraction on a time-frequency map --------------------------------------------
  * The reference crate declares rust/src/ridge/{mod,extraction}.rs and leaves them empty; the specification is
  * upstream's forward/backward penalised ridge tracking, old/ssqueezepy/ridge_extraction.py:11-232 (sequential

@@ -80,6 +80,9 @@ SIGNATURES = {
                                       c_int, c_int, c_dbl, c_u32, c_vp, c_vp]),
     "ssq_ssq_stft_host_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int, c_int,
                                       c_dbl, c_u32, c_vp]),
+    "ssq_wavelet_morlet": (c_int, [c_int, c_vp, c_i64, c_dbl, c_dbl, c_vp]),
+    "ssq_wavelet_gmw": (c_int, [c_int, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_int, c_int, c_vp]),
+    "ssq_wavelet_gmw_center_frequency": (c_int, [c_dbl, c_dbl, c_int, C.POINTER(c_dbl)]),
     "ssq_extract_ridges_batch": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_dbl, c_int, c_int, c_int, c_vp,
                                          c_vp, c_vp, c_vp]),
     "ssq_extract_ridges_host": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_dbl, c_int, c_int, c_int, c_vp, c_vp,

@@ -22,7 +22,8 @@ from ._lib import (FLAG_ADM_EXACT, FLAG_L2_NORM, FLAG_MODULATED, FLAG_NO_FLIPUD,
                    default_context, load, raise_status)
 
 __all__ = ["hello_from_bin", "stft", "ssq_stft", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt", "icwt", "issq_cwt",
-           "adm_ssq", "extract_ridges"]
+           "adm_ssq", "extract_ridges", "morlet", "morlet_freq", "morlet_time", "gmw", "gmw_freq", "gmw_time",
+           "gmw_center_frequency"]
 
 
 def _f64_1d(a, name):
@@ -350,3 +351,57 @@ def extract_ridges(Tf, scales, penalty=2.0, n_ridges=1, bw=15, transform="cwt", 
     if return_E:
         return (out + (E,)) if get_params else (out, E)
     return out
+
+
+# ---- wavelet generators (src/ssqueeze/_rs.pyi:91-132; rust/src/wavelets/{morlet,gmw}.rs) ----------------------
+def _wavelet_call(fn, kind, w, n, *args):
+    out = np.empty(n, dtype=np.complex128)
+    st = fn(kind, _ptr(w) if w is not None else C.c_void_p(0), n, *args, _ptr(out))
+    raise_status(st, None)
+    return out
+
+
+def morlet(w, mu=6.0, dtype="float64"):
+    """morlet.rs:59-76.  psi-hat(w) complex128; `dtype` is accepted and unused as in the reference."""
+    w = _f64_1d(w, "w")
+    return _wavelet_call(load().ssq_wavelet_morlet, 0, w, len(w), 1.0, float(mu))
+
+
+def morlet_freq(n=1024, scale=1.0, mu=6.0, dtype="float64"):
+    """morlet.rs:79-101: psi-hat on xifn(scale, n)."""
+    return _wavelet_call(load().ssq_wavelet_morlet, 1, None, int(n), float(scale), float(mu))
+
+
+def morlet_time(n=1024, scale=1.0, mu=6.0, dtype="float64"):
+    """morlet.rs:104-145: the time-domain wavelet."""
+    return _wavelet_call(load().ssq_wavelet_morlet, 2, None, int(n), float(scale), float(mu))
+
+
+def gmw(w, gamma=3.0, beta=60.0, norm="bandpass", order=0, dtype="float64"):
+    """gmw.rs:226-258 (ValueError for gamma <= 0, beta < 0, order < 0)."""
+    w = _f64_1d(w, "w")
+    return _wavelet_call(load().ssq_wavelet_gmw, 0, w, len(w), 1.0, float(gamma), float(beta),
+                         1 if _str(norm, "norm").lower() == "bandpass" else 0, int(order))
+
+
+def gmw_freq(n=1024, scale=1.0, gamma=3.0, beta=60.0, norm="bandpass", order=0, dtype="float64"):
+    """gmw.rs:261-281."""
+    return _wavelet_call(load().ssq_wavelet_gmw, 1, None, int(n), float(scale), float(gamma), float(beta),
+                         1 if _str(norm, "norm").lower() == "bandpass" else 0, int(order))
+
+
+def gmw_time(n=1024, scale=1.0, gamma=3.0, beta=60.0, norm="bandpass", order=0, dtype="float64"):
+    """gmw.rs:284-327."""
+    return _wavelet_call(load().ssq_wavelet_gmw, 2, None, int(n), float(scale), float(gamma), float(beta),
+                         1 if _str(norm, "norm").lower() == "bandpass" else 0, int(order))
+
+
+def gmw_center_frequency(gamma=3.0, beta=60.0, kind="peak"):
+    """gmw.rs:331-357: "peak" | "energy", anything else raises ValueError."""
+    k = {"peak": 0, "energy": 1}.get(_str(kind, "kind"), 2)
+    out = C.c_double(0.0)
+    st = load().ssq_wavelet_gmw_center_frequency(float(gamma), float(beta), k, C.byref(out))
+    if st == _lib.SSQ_EINVAL:
+        raise ValueError(f"Unknown center frequency kind: {kind}")
+    raise_status(st, None)
+    return out.value

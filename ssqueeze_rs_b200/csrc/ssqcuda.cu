@@ -1220,3 +1220,4 @@ extern "C" ssq_status ssq_stream_push_f32(ssq_stream* s, const float* d_chunk, i
 #include "cwt_host.inl"
 #include "stft_rows.inl"
 #include "ridge_host.inl"
+#include "wavelets_host.inl"

@@ -30,6 +30,8 @@
   rounding for gmw; for morlet only where psi-hat is negligible at the Nyquist bin (the Rust grid
   keeps +pi there, `wavelets/base.rs:18-33`, upstream -pi) -- rows `morlet_rows_ok`.
 
+* `upstream_wavelets.npz` -- upstream's morlet / gmw (order 0, both norms) / centre frequencies / time-domain gmw
+  at the points where the Rust generator functions (rust/src/wavelets/{morlet,gmw}.rs) coincide with them.
 * `upstream_ridges.npz` -- upstream `extract_ridges(..., parallel=False, get_params=True)`
   (`ridge_extraction.py:11-232`; the sequential JIT code: the parallel one races on the ridge index) on a
   two-chirp CWT-like map and an STFT-like map, float64 and float32, 1-3 ridges: pins oracle/ridge_oracle.py.
@@ -172,6 +174,31 @@ def upstream_cwt():
     return out
 
 
+def upstream_wavelets():
+    """Upstream's wavelets at the points where the Rust definitions (rust/src/wavelets/{morlet,gmw}.rs) coincide."""
+    from ssqueezepy import _gmw
+    from ssqueezepy.wavelets import Wavelet
+    out = {}
+    w = np.concatenate([np.linspace(-2.0, 12.0, 57), [0.0, 1e-3, 2.7144176165949063, 6.0]])
+    out["w"] = w
+    for mu in (6.0, 13.4, 5.0):
+        out[f"morlet_mu{mu}"] = np.asarray(Wavelet(("morlet", {"mu": mu, "dtype": "float64"}))(w, nohalf=True)).astype(np.complex128).ravel()
+    for (g, b) in ((3.0, 60.0), (3.0, 20.0), (2.0, 7.5)):
+        for norm in ("bandpass", "energy"):
+            f = _gmw.gmw(g, b, norm, 0, centered_scale=False, dtype="float64")
+            wp = np.where(w > 0, w, 1.0)
+            out[f"gmw_{g}_{b}_{norm}"] = np.where(w > 0, np.asarray(f(wp)), 0.0).astype(np.complex128)
+        wm, we = _gmw.morsefreq(g, b, n_out=2)
+        out[f"wc_peak_{g}_{b}"] = np.array(wm)
+        out[f"wc_energy_{g}_{b}"] = np.array(we)
+    # time domain: compute_gmw(time=True) follows the same recipe as gmw_time (gmw.rs:284-327)
+    for n in (64, 101):
+        X, x = _gmw.compute_gmw(n, 1.5, 3.0, 60.0, time=True, norm="bandpass", order=0, dtype="float64")
+        out[f"gmw_time_{n}"] = np.asarray(x).astype(np.complex128)
+        out[f"gmw_freq_{n}"] = np.asarray(X).astype(np.complex128)
+    return out
+
+
 def upstream_ridges():
     from ssqueezepy.ridge_extraction import extract_ridges
     rng = np.random.default_rng(20261019)
@@ -205,11 +232,16 @@ def upstream_ridges():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "wavelets":
+        np.savez_compressed(os.path.join(HERE, "upstream_wavelets.npz"), **upstream_wavelets())
+        print("upstream_wavelets.npz", os.path.getsize(os.path.join(HERE, "upstream_wavelets.npz")), "bytes")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ridges":  # regenerate one file only
         np.savez_compressed(os.path.join(HERE, "upstream_ridges.npz"), **upstream_ridges())
         print("upstream_ridges.npz", os.path.getsize(os.path.join(HERE, "upstream_ridges.npz")), "bytes")
         sys.exit(0)
     np.savez_compressed(os.path.join(HERE, "upstream_ridges.npz"), **upstream_ridges())
+    np.savez_compressed(os.path.join(HERE, "upstream_wavelets.npz"), **upstream_wavelets())
     np.savez_compressed(os.path.join(HERE, "upstream_components.npz"), **upstream_components())
     np.savez_compressed(os.path.join(HERE, "upstream_even512.npz"), **upstream_even512())
     np.savez_compressed(os.path.join(HERE, "upstream_cwt.npz"), **upstream_cwt())
