@@ -164,8 +164,9 @@ ssq_status ssq_ssq_cwt_f64(ssq_ctx* ctx, const double* x, int64_t n, int wavelet
 
 /* `icwt`: cwt.rs:548-718, a #[pyfunction] the reference module never registers.
  * One-integral branch (:590-627, the default): x[j] = (2/adm) dj sum_i Re Wx[i,j] norm_i + x_mean.
- * one_int == 0 (two-integral branch, :629-712: per scale FFT(Wx[i]) conj(psi-hat_i) -> IFFT / x_len / scale, summed
- * in the frequency domain here) is built for x_len == n_cols == 2^k; other lengths return SSQ_EUNSUPPORTED.
+ * one_int == 0 (two-integral branch, :629-712: per scale FFT(Wx[i, :x_len]) conj(psi-hat_i) -> IFFT / x_len / scale,
+ * summed in the frequency domain here, one inverse transform): any x_len <= n_cols (Bluestein for lengths that are
+ * not powers of two).
  * Wx complex128 [ns, n_cols] -> x float64 [x_len] (x_len <= 0: n_cols).
  * flags: SSQ_FLAG_L2_NORM, SSQ_FLAG_ADM_EXACT. */
 ssq_status ssq_icwt_f64(ssq_ctx* ctx, const double* Wx, int64_t ns, int64_t n_cols, int wavelet,

@@ -252,9 +252,9 @@ def ssq_cwt(x, wavelet="gmw", scales=None, fs=None, t=None, ssq_freqs=None, nv=3
 def icwt(Wx, wavelet="gmw", scales=None, nv=None, one_int=True, x_len=None, x_mean=0.0, padtype="reflect",
          rpadded=False, l1_norm=True, exact_adm=False):
     """cwt.rs:548-566 (declared in src/ssqueeze/_rs.pyi:62-73, never registered by lib.rs:25-32).
-    One-integral reconstruction (default) or the two-integral branch (`one_int=False`; built for power-of-two
-    `x_len == Wx.shape[1]`, e.g. `rpadded` coefficients); `nv`, `padtype`, `rpadded` are accepted and unused as in
-    the reference.
+    One-integral reconstruction (default) or the two-integral branch (`one_int=False`, any `x_len <= Wx.shape[1]`:
+    row FFTs, Bluestein for lengths that are not powers of two); `nv`, `padtype`, `rpadded` are accepted and unused as
+    in the reference.
     `exact_adm=True` (not in the reference) divides by the wavelet's true admissibility integral
     (`adm_ssq`) instead of the placeholders 0.776 / 1.0 of cwt.rs:579-583, so that `icwt(cwt(x))` returns x."""
     if not isinstance(Wx, np.ndarray) or Wx.ndim != 2 or Wx.dtype != np.complex128:

@@ -261,6 +261,8 @@ static ssq_status cwt_upload_scales(ssq_ctx* ctx, const double* scales, int64_t 
   return SSQ_OK;
 }
 
+static ssq_status rows_bluestein_tables(ssq_ctx* ctx, int N, int64_t M, const float2** d_chirp, const float2** d_filt);  // stft_rows.inl
+
 static ssq_status cwt_prepare(ssq_ctx* ctx, const CwtCall& c, int* log2L, FftPlanHost* pl, const float2** lo,
                               const float2** hi, int* tw_s, const float** d_scales, float2** xhat, float2** ws0,
                               float2** ws1, int64_t* max_rows) {
@@ -541,60 +543,113 @@ extern "C" ssq_status ssq_icwt_batch_f32(ssq_ctx* ctx, const float* d_Wx, int64_
   const double dj = (ns > 1 && scales[1] > scales[0]) ? std::log(scales[1] / scales[0]) : 0.1;     // :595-599
   const double final_norm = (2.0 / adm) * dj;
   if (!one_int) {
-    // Two-integral branch (cwt.rs:629-712): per scale FFT(Wx[i]) * conj(psi-hat_i) -> IFFT, real part / x_len /
-    // scale, summed over the scales.  By linearity the sum is taken in the frequency domain and ONE inverse
-    // transform follows.  The reference transforms rows of arbitrary length x_len (rustfft); here x_len must be
-    // a power of two equal to the row length (e.g. rpadded Wx).
+    // Two-integral branch (cwt.rs:629-712): per scale FFT(Wx[i, :x_len]) * conj(psi-hat_i) -> IFFT, real part / x_len
+    // / scale, summed over the scales.  By linearity the sum is taken in the frequency domain and ONE inverse
+    // transform follows.  Any x_len (rustfft takes any length): powers of two run the row FFT directly, other
+    // lengths through Bluestein's identity on rows of M = 2^k >= 2 x_len - 1 (stft_rows.inl).
+    const int64_t N = x_len;
+    if (N < 2) return ssq_fail(ctx, SSQ_EINVAL, "icwt: x_len %lld", (long long)N);
+    const bool pow2 = (N & (N - 1)) == 0;
     int l2 = 0;
-    while (((int64_t)1 << l2) < x_len) ++l2;
-    if (x_len != n_cols || ((int64_t)1 << l2) != x_len || l2 < 1 || l2 > 27)
-      return ssq_fail(ctx, SSQ_EUNSUPPORTED,
-                      "icwt: the two-integral branch (cwt.rs:629-712) is built for x_len == Wx.shape[1] == 2^k only "
-                      "(got x_len %lld, %lld columns); use one_int=True", (long long)x_len, (long long)n_cols);
-    const int64_t L = x_len;
+    int64_t M = 1;
+    while (M < (pow2 ? N : 2 * N - 1)) {
+      M <<= 1;
+      ++l2;
+    }
+    if (l2 > 27) return ssq_fail(ctx, SSQ_EUNSUPPORTED, "icwt: rows of 2^%d points", l2);
     const FftPlanHost pl = fft_plan(l2);
     const float2 *lo, *hi;
     int tw_s;
     SSQ_TRY(cwt_twiddles(ctx, l2, &lo, &hi, &tw_s));
     SSQ_TRY(cwt_upload_scales(ctx, scales, ns));
-    const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>(ns, ((int64_t)1 << 30) / (L * 8)));
-    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft0, (size_t)ns * L * sizeof(float2)));
-    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft1, (size_t)2 * max_rows * L * sizeof(float2)));
-    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, (size_t)2 * L * sizeof(float2)));
+    const float2 *d_chirp = nullptr, *d_filt = nullptr;
+    if (!pow2) SSQ_TRY(rows_bluestein_tables(ctx, (int)N, M, &d_chirp, &d_filt));
+    const int64_t max_rows = std::max<int64_t>(1, std::min<int64_t>(ns, ((int64_t)1 << 30) / (M * 8)));
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft0, (size_t)ns * M * sizeof(float2)));
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_fft1, (size_t)2 * max_rows * M * sizeof(float2)));
+    SSQ_TRY(devbuf_reserve(ctx, ctx->ws_aux0, (size_t)3 * M * sizeof(float2) + (pow2 ? 0 : (size_t)max_rows * M * sizeof(float2))));
     float2* What = (float2*)ctx->ws_fft0.p;
     float2* ws0 = (float2*)ctx->ws_fft1.p;
-    float2* ws1 = ws0 + (size_t)max_rows * L;
+    float2* ws1 = ws0 + (size_t)max_rows * M;
     float2* S = (float2*)ctx->ws_aux0.p;
-    float2* S2 = S + L;
+    float2* S2 = S + M;
+    float2* S3 = S2 + M;
+    float2* tmp = S3 + M;  // Bluestein: forward spectra of a batch of rows
     FftPass B;
-    memset(&B, 0, sizeof(B));
-    B.tw_lo = lo;
-    B.tw_hi = hi;
-    B.tw_s = tw_s;
     const double K = cwt_denorm_constant(wavelet);
+    const int wav = wavelet == SSQ_WAVELET_MORLET ? SSQ_WAVELET_MORLET : SSQ_WAVELET_GMW;
     SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     for (int64_t ch = 0; ch < channels; ++ch) {
-      B.sign = -1;
       for (int64_t r0 = 0; r0 < ns; r0 += max_rows) {
         const int rows = (int)std::min<int64_t>(max_rows, ns - r0);
-        B.in = (const float2*)d_Wx + ((size_t)ch * ns + r0) * L;
-        B.out = What + (size_t)r0 * L;
-        B.row0 = r0;
+        memset(&B, 0, sizeof(B));
+        B.tw_lo = lo;
+        B.tw_hi = hi;
+        B.tw_s = tw_s;
+        B.sign = -1;
+        B.load_mode = 6;
+        B.in = (const float2*)d_Wx + ((size_t)ch * ns + r0) * n_cols;
+        B.fr_ld = n_cols;
+        B.fr_nfft = (int)N;
+        B.fr_chirp = d_chirp;
+        B.out = pow2 ? What + (size_t)r0 * M : tmp;
         SSQ_TRY(fft_run(ctx, pl, B, rows, ws0, ws1));
+        if (!pow2) {
+          FftPass I;
+          memset(&I, 0, sizeof(I));
+          I.tw_lo = lo;
+          I.tw_hi = hi;
+          I.tw_s = tw_s;
+          I.sign = +1;
+          I.load_mode = 4;
+          I.in = tmp;
+          I.mul = d_filt;
+          I.out = What + (size_t)r0 * M;
+          SSQ_TRY(fft_run(ctx, pl, I, rows, ws0, ws1));
+        }
       }
-      icwt2_accum_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(
-          What, (int)ns, (int)L, (const float*)ctx->cwt_scales.p, wavelet == SSQ_WAVELET_MORLET ? SSQ_WAVELET_MORLET : SSQ_WAVELET_GMW, S);
+      // S[k] = sum_i What_i[k] (c[k]) psi-hat_i / scale_i, k < N
+      icwt2_accum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(What, M, d_chirp, (int)ns, (int)N,
+                                                                              (const float*)ctx->cwt_scales.p, wav, S);
       SSQ_TRY(ssq_check_launch(ctx, "icwt2_accum_kernel"));
-      B.sign = +1;
-      B.in = S;
-      B.out = S2;
-      B.row0 = 0;
-      SSQ_TRY(fft_run(ctx, pl, B, 1, ws0, ws1));
-      icwt2_finalize_kernel<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(
-          S2, L, (float)(K * final_norm / (double)L), (float)x_mean, d_x + (size_t)ch * L);
+      // inverse DFT of length N: directly, or as conj(DFT(conj S)) through the same Bluestein rows
+      memset(&B, 0, sizeof(B));
+      B.tw_lo = lo;
+      B.tw_hi = hi;
+      B.tw_s = tw_s;
+      if (pow2) {
+        B.sign = +1;
+        B.in = S;
+        B.out = S2;
+        SSQ_TRY(fft_run(ctx, pl, B, 1, ws0, ws1));
+      } else {
+        B.sign = -1;
+        B.load_mode = 6;
+        B.in = S;
+        B.fr_ld = M;
+        B.fr_nfft = (int)N;
+        B.fr_chirp = d_chirp;
+        B.conj_in = 1;
+        B.out = S3;
+        SSQ_TRY(fft_run(ctx, pl, B, 1, ws0, ws1));
+        FftPass I;
+        memset(&I, 0, sizeof(I));
+        I.tw_lo = lo;
+        I.tw_hi = hi;
+        I.tw_s = tw_s;
+        I.sign = +1;
+        I.load_mode = 4;
+        I.in = S3;
+        I.mul = d_filt;
+        I.out = S2;
+        SSQ_TRY(fft_run(ctx, pl, I, 1, ws0, ws1));
+      }
+      // x = Re(.) K final_norm / N + x_mean (the conjugation of the Bluestein route leaves the real part alone)
+      icwt2_finalize_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(
+          S2, pow2 ? nullptr : d_chirp, N, (float)(K * final_norm / (double)N), (float)x_mean, d_x + (size_t)ch * N);
       SSQ_TRY(ssq_check_launch(ctx, "icwt2_finalize_kernel"));
     }
-    ctx->last_kernel = "icwt2_accum_kernel";
+    ctx->last_kernel = pow2 ? "icwt2_accum_kernel" : "icwt2_accum_kernel<bluestein>";
     SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
     return SSQ_OK;

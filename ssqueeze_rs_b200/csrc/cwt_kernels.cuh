@@ -122,7 +122,7 @@ struct FftPass {
   int tw_s;
   int64_t row0;       // global row index of row 0 of this launch
   // ---- load functor -------------------------------------------------------------
-  int load_mode;      // 0 plain, 1 padded real signal, 2 x-hat * psi-hat, 3 windowed STFT frame, 4 plain * mul[idx], 5 istft column
+  int load_mode;      // 0 plain, 1 padded real signal, 2 x-hat * psi-hat, 3 windowed STFT frame, 4 plain * mul[idx], 5 istft column, 6 strided rows
   const float* x;     // [channels, x_stride] (mode 1)
   int64_t x_stride, n;
   int padtype;
@@ -144,6 +144,9 @@ struct FftPass {
   int64_t fr_ld;
   // mode 4: in[row][idx] * mul[idx] (Bluestein: spectrum of the chirp filter, 1/M folded in)
   const float2* mul;
+  // mode 6: rows of fr_nfft points with row stride fr_ld inside rows of L: in[row * fr_ld + idx] (conjugated when
+  // conj_in) * fr_chirp[idx] (when given), zero beyond fr_nfft (icwt two-integral branch at any row length)
+  int conj_in;
   // ---- store functor ------------------------------------------------------------
   int store_mode;     // 0 plain, 1 final: scaled, unpadded rows to outW / outD, 2: fused ssq_cwt epilogue
   float2* outW;       // [channels, ns, out_cols]
@@ -209,6 +212,13 @@ __device__ __forceinline__ float2 pass_load(const FftPass& P, int row, int64_t i
   const int64_t g = P.row0 + row;
   if (P.load_mode == 1) return make_float2(cwt_sample(P, (int)g, idx, L), 0.f);
   if (P.load_mode == 4) return cmulf(P.in[(size_t)row * L + idx], __ldg(P.mul + idx));
+  if (P.load_mode == 6) {
+    if (idx >= P.fr_nfft) return make_float2(0.f, 0.f);
+    float2 v = P.in[(size_t)row * P.fr_ld + idx];
+    if (P.conj_in) v.y = -v.y;
+    if (P.fr_chirp) v = cmulf(v, __ldg(P.fr_chirp + idx));
+    return v;
+  }
   if (P.load_mode == 5) {
     if (idx >= P.fr_nfft) return make_float2(0.f, 0.f);
     const int64_t ch = g / P.fr_count, frame = P.fr_first + (g - ch * P.fr_count);
@@ -690,29 +700,34 @@ __global__ void issq_cwt_components_kernel(const float2* __restrict__ Tx, int ns
 //   S[k] = sum_i FFT(Wx[i])[k] * psi-hat(scale_i xi_k) / scale_i   (psi-hat real; peak-normalised here, the constant
 //   goes into the final factor), then x = Re(IFFT(S)) * norm + x_mean.
 // ------------------------------------------------------------------------------------
-__global__ void icwt2_accum_kernel(const float2* __restrict__ What, int ns, int L, const float* __restrict__ scales,
-                                   int wavelet, float2* __restrict__ S) {
+// What: [ns] rows of stride ld (spectra of the rows; times zmul[k] when given: Bluestein); N: transform length
+__global__ void icwt2_accum_kernel(const float2* __restrict__ What, int64_t ld, const float2* __restrict__ zmul, int ns,
+                                   int N, const float* __restrict__ scales, int wavelet, float2* __restrict__ S) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= L) return;
-  // wavelets/base.rs:18-33: xi_k = 2 pi k / L up to and including the Nyquist bin, 2 pi (k - L) / L above
-  const float xi = 6.283185307179586f * (float)(k <= (L >> 1) ? k : k - L) / (float)L;
+  if (k >= N) return;
+  // wavelets/base.rs:18-33: xi_k = 2 pi k / N up to and including the Nyquist bin, 2 pi (k - N) / N above
+  const float xi = 6.283185307179586f * (float)(k <= (N >> 1) ? k : k - N) / (float)N;
   float2 acc = make_float2(0.f, 0.f);
   for (int i = 0; i < ns; ++i) {
     const float sc = __ldg(scales + i);
     const float ps = psihat(wavelet, sc * xi);
     if (ps != 0.f) {
-      const float2 w = What[(size_t)i * L + k];
+      const float2 w = What[(size_t)i * ld + k];
       const float f = ps / sc;  // 1/scale for both norms (cwt.rs:684-688: 1/scale and 1/sqrt(scale)^2)
       acc.x = fmaf(w.x, f, acc.x);
       acc.y = fmaf(w.y, f, acc.y);
     }
   }
+  if (zmul) acc = cmulf(acc, __ldg(zmul + k));
   S[k] = acc;
 }
 
-__global__ void icwt2_finalize_kernel(const float2* __restrict__ s, int64_t L, float norm, float x_mean,
-                                      float* __restrict__ x) {
+__global__ void icwt2_finalize_kernel(const float2* __restrict__ s, const float2* __restrict__ zmul, int64_t L,
+                                      float norm, float x_mean, float* __restrict__ x) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < L) x[j] = fmaf(s[j].x, norm, x_mean);
+  if (j >= L) return;
+  float2 v = s[j];
+  if (zmul) v = cmulf(v, __ldg(zmul + j));
+  x[j] = fmaf(v.x, norm, x_mean);
 }
 

@@ -16,6 +16,34 @@ struct RowsTables {
   int64_t M = 0;
 };
 
+// Bluestein tables of length N on rows of M points, cached by N: chirp c[n] = exp(-i pi n^2 / N) and the spectrum of
+// the chirp filter conj(c[|m|]) (1/M of the inverse row FFT folded in), both from double.
+static ssq_status rows_bluestein_tables(ssq_ctx* ctx, int N, int64_t M, const float2** d_chirp, const float2** d_filt) {
+  if (ctx->rows_n != N || !ctx->rows_tab.p) {
+    std::vector<ssqhost::cd> h((size_t)M, ssqhost::cd(0.0, 0.0));
+    std::vector<float> t((size_t)2 * (N + M));
+    for (int j = 0; j < N; ++j) {
+      const ssqhost::cd c = ssqhost::chirp(j, N);
+      t[(size_t)2 * j] = (float)c.real();
+      t[(size_t)2 * j + 1] = (float)c.imag();
+      h[(size_t)j] = std::conj(c);
+      if (j) h[(size_t)(M - j)] = std::conj(c);
+    }
+    ssqhost::dft(h, false);
+    for (int64_t i = 0; i < M; ++i) {
+      t[(size_t)2 * (N + i)] = (float)(h[(size_t)i].real() / (double)M);
+      t[(size_t)2 * (N + i) + 1] = (float)(h[(size_t)i].imag() / (double)M);
+    }
+    SSQ_TRY(devbuf_reserve(ctx, ctx->rows_tab, t.size() * sizeof(float)));
+    SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->rows_tab.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->rows_n = N;
+  }
+  *d_chirp = (const float2*)ctx->rows_tab.p;
+  *d_filt = *d_chirp + N;
+  return SSQ_OK;
+}
+
 static ssq_status stft_rows_run(ssq_ctx* ctx, StftParams P /* by value: per-batch copies */, bool* done) {
   *done = false;
   const int N = P.n_fft;
@@ -33,32 +61,8 @@ static ssq_status stft_rows_run(ssq_ctx* ctx, StftParams P /* by value: per-batc
   int tw_s;
   // (the CWT twiddle cache is keyed by the row length; a CWT call after this one rebuilds it)
   SSQ_TRY(cwt_twiddles(ctx, l2, &lo, &hi, &tw_s));
-  // Bluestein tables, cached by n_fft
   const float2 *d_chirp = nullptr, *d_filt = nullptr;
-  if (!pow2) {
-    if (ctx->rows_n != N || !ctx->rows_tab.p) {
-      std::vector<ssqhost::cd> h((size_t)M, ssqhost::cd(0.0, 0.0));
-      std::vector<float> t((size_t)2 * (N + M));
-      for (int j = 0; j < N; ++j) {
-        const ssqhost::cd c = ssqhost::chirp(j, N);
-        t[(size_t)2 * j] = (float)c.real();
-        t[(size_t)2 * j + 1] = (float)c.imag();
-        h[(size_t)j] = std::conj(c);
-        if (j) h[(size_t)(M - j)] = std::conj(c);
-      }
-      ssqhost::dft(h, false);
-      for (int64_t i = 0; i < M; ++i) {  // 1/M of the inverse row FFT folded in
-        t[(size_t)2 * (N + i)] = (float)(h[(size_t)i].real() / (double)M);
-        t[(size_t)2 * (N + i) + 1] = (float)(h[(size_t)i].imag() / (double)M);
-      }
-      SSQ_TRY(devbuf_reserve(ctx, ctx->rows_tab, t.size() * sizeof(float)));
-      SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->rows_tab.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
-      ctx->rows_n = N;
-    }
-    d_chirp = (const float2*)ctx->rows_tab.p;
-    d_filt = d_chirp + N;
-  }
+  if (!pow2) SSQ_TRY(rows_bluestein_tables(ctx, N, M, &d_chirp, &d_filt));
   // batches of rows: spectra + (Bluestein: a second row buffer) + ping-pong workspaces of the passes
   const size_t row_bytes = (size_t)M * sizeof(float2);
   const int64_t rows_max = std::max<int64_t>(2, (int64_t)(((size_t)512 << 20) / row_bytes));
@@ -183,30 +187,7 @@ static ssq_status istft_rows_run(ssq_ctx* ctx, IstftParams P, bool* done) {
   int tw_s;
   SSQ_TRY(cwt_twiddles(ctx, l2, &lo, &hi, &tw_s));
   const float2 *d_chirp = nullptr, *d_filt = nullptr;
-  if (!pow2) {
-    if (ctx->rows_n != N || !ctx->rows_tab.p) {
-      std::vector<ssqhost::cd> h((size_t)M, ssqhost::cd(0.0, 0.0));
-      std::vector<float> t((size_t)2 * (N + M));
-      for (int j = 0; j < N; ++j) {
-        const ssqhost::cd c = ssqhost::chirp(j, N);
-        t[(size_t)2 * j] = (float)c.real();
-        t[(size_t)2 * j + 1] = (float)c.imag();
-        h[(size_t)j] = std::conj(c);
-        if (j) h[(size_t)(M - j)] = std::conj(c);
-      }
-      ssqhost::dft(h, false);
-      for (int64_t i = 0; i < M; ++i) {
-        t[(size_t)2 * (N + i)] = (float)(h[(size_t)i].real() / (double)M);
-        t[(size_t)2 * (N + i) + 1] = (float)(h[(size_t)i].imag() / (double)M);
-      }
-      SSQ_TRY(devbuf_reserve(ctx, ctx->rows_tab, t.size() * sizeof(float)));
-      SSQ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      SSQ_CUDA_TRY(ctx, cudaMemcpy(ctx->rows_tab.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
-      ctx->rows_n = N;
-    }
-    d_chirp = (const float2*)ctx->rows_tab.p;
-    d_filt = d_chirp + N;
-  }
+  if (!pow2) SSQ_TRY(rows_bluestein_tables(ctx, N, M, &d_chirp, &d_filt));
   const size_t row_bytes = (size_t)M * sizeof(float2);
   const int64_t rows_max = std::max<int64_t>(2, (int64_t)(((size_t)512 << 20) / row_bytes));
   const int64_t cc_max = std::min<int64_t>(P.channels, rows_max);

@@ -265,8 +265,6 @@ def test_icwt_one_integral():
         rs.icwt(Wx)                                   # "Scales must be provided"
     with pytest.raises(PanicException):
         rs.icwt(Wx, "gmw", sc, x_len=5000)            # index out of bounds in the reference
-    with pytest.raises(SsqError):
-        rs.icwt(Wx, "gmw", sc, one_int=False)         # two-integral branch not built
 
 
 def test_admissibility_icwt_exact_and_issq_cwt():
@@ -409,6 +407,15 @@ def test_icwt_two_integral_power_of_two():
                 xo = O.icwt(Wx, wav, sc, one_int=False, l1_norm=l1, x_mean=-0.5)
                 assert xr.shape == (L,)
                 assert np.abs(xr - xo).max() < 2 * RTOL * np.abs(xo + 0.5).max(), (N, wav, l1)
-    Wx, _, _ = rs.cwt(rng.standard_normal(3000), "gmw", 2.0 ** np.linspace(1, 8, 30), fs=1.0)
-    with pytest.raises(SsqError):
-        rs.icwt(Wx, "gmw", 2.0 ** np.linspace(1, 8, 30), one_int=False)  # 3000 columns: not a power of two
+    # any row length (rustfft takes any): 3000, 777 and 4097 columns through Bluestein; x_len shorter than the rows
+    for N, sc in ((3000, 2.0 ** np.linspace(1, 8, 30)), (777, 2.0 ** np.linspace(1, 6, 12)), (4097, 2.0 ** np.linspace(1, 9, 20))):
+        x = rng.standard_normal(N)
+        for wav in ("gmw", "morlet"):
+            Wx, _, _ = rs.cwt(x, wav, sc, fs=1.0)
+            for xl in (None, N // 3):
+                xr = rs.icwt(Wx, wav, sc, one_int=False, x_mean=0.125, x_len=xl)
+                from ssqueeze_rs_b200 import _lib
+                assert "icwt2" in _lib.default_context().last_kernel_name()
+                xo = O.icwt(Wx, wav, sc, one_int=False, x_mean=0.125, x_len=xl)
+                assert xr.shape == xo.shape
+                assert np.abs(xr - xo).max() < 2 * RTOL * np.abs(xo - 0.125).max(), (N, wav, xl)
