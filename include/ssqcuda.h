@@ -89,7 +89,9 @@ ssq_status ssq_ctx_synchronize(ssq_ctx* ctx);
 /* kernel-selection switches for measurements and cross-checks; none changes results beyond
  * fp32 rounding.  Every option is seeded once, at ssq_ctx_create, from the environment variable SSQ_<NAME>.
  * names: no_h32r, h32r_nw (4|8), no_r1024, no_r256, istft_nw (4|8), no_fft128, fft128_tc (32|64),
- * no_cwt_prune, no_cwt_fused, cwt_ws_mb. */
+ * no_cwt_prune, no_cwt_fused, cwt_ws_mb.
+ * One option does change results: upstream_framing = 1 frames the STFT family as upstream ssqueezepy does (left pad
+ * n_fft / 2 instead of the crate's (n_fft - 1) / 2, stft_utils.rs:22) -- the upstream-compatible mode, SURVEY 8f rank 3. */
 ssq_status ssq_ctx_set_option(ssq_ctx* ctx, const char* name, int64_t value);
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 uint64_t ssq_ctx_launch_count(const ssq_ctx* ctx);

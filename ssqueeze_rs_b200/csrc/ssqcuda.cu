@@ -79,7 +79,7 @@ extern "C" ssq_status ssq_ctx_create(int device, ssq_ctx** out) {
   c->stream = c->own_stream;
   // switches: read from the environment once, here (never on the launch path)
   static const char* const names[] = {"no_h32r", "h32r_nw", "no_r1024", "no_r256", "istft_nw", "no_fft128",
-                                      "fft128_tc", "no_cwt_prune", "no_cwt_fused", "cwt_ws_mb"};
+                                      "fft128_tc", "no_cwt_prune", "no_cwt_fused", "cwt_ws_mb", "upstream_framing"};
   for (const char* nm : names) {
     std::string env = "SSQ_";
     for (const char* q = nm; *q; ++q) env += (char)toupper((unsigned char)*q);
@@ -103,6 +103,7 @@ extern "C" ssq_status ssq_ctx_set_option(ssq_ctx* ctx, const char* name, int64_t
   else if (n == "no_cwt_prune") o.no_cwt_prune = value != 0;
   else if (n == "no_cwt_fused") o.no_cwt_fused = value != 0;
   else if (n == "cwt_ws_mb") o.cwt_ws_mb = value > 0 ? value : 0;
+  else if (n == "upstream_framing") o.upstream_framing = value != 0;
   else return ssq_fail(ctx, SSQ_EINVAL, "ssq_ctx_set_option: unknown option '%s'", name);
   return SSQ_OK;
 }
@@ -424,7 +425,7 @@ static ssq_status run_stft_family(ssq_ctx* ctx, const StftCall& c) {
   P.n_frames = n_frames;
   P.frame0 = c.frame0;
   P.x_origin = c.x_origin;
-  P.left = (N - 1) / 2;
+  P.left = ctx->opt.upstream_framing ? N / 2 : (N - 1) / 2;  // stft_utils.rs:22 | old/ssqueezepy/utils/common.py:116-120
   P.padtype = c.padtype == SSQ_PAD_ZERO ? SSQ_PAD_ZERO : SSQ_PAD_REFLECT;
   P.win = T.win;
   P.dwin = T.dwin;
@@ -556,6 +557,10 @@ extern "C" ssq_status ssq_stft_batch_f32(ssq_ctx* ctx, const float* d_x, int64_t
   return run_stft_family(ctx, c);
 }
 
+static inline int istft_left(const ssq_ctx* ctx, int n_fft) {
+  return ctx->opt.upstream_framing ? n_fft / 2 : (n_fft - 1) / 2;
+}
+
 extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64_t channels, int64_t n_freqs,
                                           int64_t n_frames, const double* window, int64_t win_n, int n_fft,
                                           int hop, int64_t n_out, int win_exp, float* d_xout) {
@@ -611,7 +616,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
     ctx->ev_valid = true;
     dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
     istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
-                                                      (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+                                                      istft_left(ctx, n_fft), max_hops, T.wpow, d_xout);
     SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
     return SSQ_OK;
   }
@@ -644,7 +649,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
       ctx->ev_valid = true;
       dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
       istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
-                                                        (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+                                                        istft_left(ctx, n_fft), max_hops, T.wpow, d_xout);
       SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
       return SSQ_OK;
     }
@@ -678,7 +683,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
       ctx->ev_valid = true;
       dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
       istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
-                                                        (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+                                                        istft_left(ctx, n_fft), max_hops, T.wpow, d_xout);
       SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
       return SSQ_OK;
     }
@@ -708,7 +713,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
       ctx->ev_valid = true;
       dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
       istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
-                                                        (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+                                                        istft_left(ctx, n_fft), max_hops, T.wpow, d_xout);
       SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
       return SSQ_OK;
     }
@@ -728,7 +733,7 @@ extern "C" ssq_status ssq_istft_batch_f32(ssq_ctx* ctx, const float* d_Sx, int64
   ctx->ev_valid = true;
   dim3 g((unsigned)((n_out + ISTFT_FIN_PER_BLOCK - 1) / ISTFT_FIN_PER_BLOCK), (unsigned)channels);
   istft_finalize_kernel<<<g, 256, 0, ctx->stream>>>((const float*)ctx->ws_misc.p, L, n_out, n_fft, hop,
-                                                    (n_fft - 1) / 2, max_hops, T.wpow, d_xout);
+                                                    istft_left(ctx, n_fft), max_hops, T.wpow, d_xout);
   SSQ_TRY(ssq_check_launch(ctx, "istft_finalize_kernel"));
   return SSQ_OK;
 }
@@ -1096,7 +1101,7 @@ extern "C" ssq_status ssq_stream_create(ssq_ctx* ctx, int64_t channels, int64_t 
   s->wfit = ssqhost::fit_window(window, win_n, n_fft);
   s->n_fft = n_fft;
   s->hop = hop;
-  s->left = (n_fft - 1) / 2;
+  s->left = ctx->opt.upstream_framing ? n_fft / 2 : (n_fft - 1) / 2;
   s->padtype = padtype;
   s->squeezing = squeezing;
   s->fs = fs;

@@ -30,6 +30,8 @@
   rounding for gmw; for morlet only where psi-hat is negligible at the Nyquist bin (the Rust grid
   keeps +pi there, `wavelets/base.rs:18-33`, upstream -pi) -- rows `morlet_rows_ok`.
 
+* `upstream_compat.npz` -- upstream's stft / ssq_stft / istft / issq_stft with upstream's own conventions (left pad
+  n_fft // 2, modulated, dpss / string / array windows), every frame: pins the upstream-compatible mode.
 * `upstream_wavelets.npz` -- upstream's morlet / gmw (order 0, both norms) / centre frequencies / time-domain gmw
   at the points where the Rust generator functions (rust/src/wavelets/{morlet,gmw}.rs) coincide with them.
 * `upstream_ridges.npz` -- upstream `extract_ridges(..., parallel=False, get_params=True)`
@@ -174,6 +176,36 @@ def upstream_cwt():
     return out
 
 
+def upstream_compat():
+    """Upstream's own stft / ssq_stft / istft / issq_stft (old/ssqueezepy/_stft.py, _ssq_stft.py) with their default
+    conventions -- even and odd n_fft, every frame including the padded ones, modulated True and False, array / string
+    / default (dpss) windows: the pin of the upstream-compatible mode (ssqueeze_rs_b200/compat.py)."""
+    import ssqueezepy as S
+    rng = np.random.default_rng(20261020)
+    out = {}
+    cases = []
+    specs = [(400, 128, 4, True, "array", 1.0), (400, 128, 4, False, "array", 1.0), (300, 120, 1, True, "hann", 1.0),
+             (301, 121, 3, True, None, 1.0), (300, 64, 1, True, "array", 250.0), (1000, 512, 32, True, "array", 1.0),
+             (257, 60, 2, False, "hamming", 1.0)]
+    for ci, (N, n_fft, hop, mod, wkind, fs) in enumerate(specs):
+        x = rng.standard_normal(N)
+        window = np.hanning(n_fft + 2)[1:-1].copy() if wkind == "array" else wkind
+        kw = dict(window=window, n_fft=n_fft, hop_len=hop, modulated=mod)
+        Tx, Sx, ssqf, Sfs, w, dSx = S.ssq_stft(x, fs=fs, dtype="float64", get_w=True, get_dWx=True, **kw)
+        xr = S.istft(Sx, N=N, **kw)
+        p = f"k{ci}_"
+        out[p + "x"] = x
+        out[p + "Tx"], out[p + "Sx"], out[p + "dSx"], out[p + "w"] = (np.asarray(a) for a in (Tx, Sx, dSx, w))
+        out[p + "ssq_freqs"], out[p + "Sfs"] = np.asarray(ssqf), np.asarray(Sfs)
+        out[p + "istft"] = np.asarray(xr)
+        out[p + "window_fit"] = np.asarray(S._stft.get_window(window, n_fft if not isinstance(window, np.ndarray) else len(window), n_fft, dtype="float64"))
+        if hop == 1 and mod:
+            out[p + "issq"] = np.asarray(S.issq_stft(Tx, window=window, n_fft=n_fft))
+        cases.append((N, n_fft, hop, int(mod), {"array": 0, "hann": 1, None: 2, "hamming": 3}[wkind], fs))
+    out["cases"] = np.array(cases, dtype=np.float64)
+    return out
+
+
 def upstream_wavelets():
     """Upstream's wavelets at the points where the Rust definitions (rust/src/wavelets/{morlet,gmw}.rs) coincide."""
     from ssqueezepy import _gmw
@@ -232,6 +264,10 @@ def upstream_ridges():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "compat":
+        np.savez_compressed(os.path.join(HERE, "upstream_compat.npz"), **upstream_compat())
+        print("upstream_compat.npz", os.path.getsize(os.path.join(HERE, "upstream_compat.npz")), "bytes")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "wavelets":
         np.savez_compressed(os.path.join(HERE, "upstream_wavelets.npz"), **upstream_wavelets())
         print("upstream_wavelets.npz", os.path.getsize(os.path.join(HERE, "upstream_wavelets.npz")), "bytes")
@@ -242,6 +278,7 @@ if __name__ == "__main__":
         sys.exit(0)
     np.savez_compressed(os.path.join(HERE, "upstream_ridges.npz"), **upstream_ridges())
     np.savez_compressed(os.path.join(HERE, "upstream_wavelets.npz"), **upstream_wavelets())
+    np.savez_compressed(os.path.join(HERE, "upstream_compat.npz"), **upstream_compat())
     np.savez_compressed(os.path.join(HERE, "upstream_components.npz"), **upstream_components())
     np.savez_compressed(os.path.join(HERE, "upstream_even512.npz"), **upstream_even512())
     np.savez_compressed(os.path.join(HERE, "upstream_cwt.npz"), **upstream_cwt())
