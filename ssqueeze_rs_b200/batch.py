@@ -115,12 +115,14 @@ class Engine:
         self.stft_ptr(x.data_ptr(), ch, n, window, n_fft, hop_len, out.data_ptr(), padtype, x_stride=x.stride(0))
         return out
 
-    def istft(self, Sx, window, n_fft, hop_len, N=None, win_exp=1):
+    def istft(self, Sx, window, n_fft, hop_len, N=None, win_exp=1, out=None):
         import torch
         assert Sx.is_cuda and Sx.dtype == torch.complex64 and Sx.dim() == 3 and Sx.is_contiguous()
         ch, nfq, nfr = Sx.shape
         n_out = N or hop_len * nfr
-        out = torch.empty((ch, n_out), dtype=torch.float32, device=Sx.device)
+        if out is None:
+            out = torch.empty((ch, n_out), dtype=torch.float32, device=Sx.device)
+        assert out.shape == (ch, n_out) and out.dtype == torch.float32 and out.is_contiguous()
         self._bind_stream()
         self.istft_ptr(Sx.data_ptr(), ch, nfq, nfr, window, n_fft, hop_len, n_out, out.data_ptr(), win_exp)
         return out
