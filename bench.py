@@ -483,13 +483,66 @@ def side_ridges_e2e(torch, eng, dev, rank, world, stream, g, cpu, scale=1.0):
     return rec
 
 
-def side_configs(torch, eng, dev, rank, world, stream, cpu, scale=1.0):
+def side_feeder_e2e(torch, eng, dev, rank, world, stream, g, cpu, scale=1.0):
+    """The reader half of the streaming path: an interleaved int16 (samples, channels) recording in
+    PAGEABLE host memory -- what a memory-mapped probe file is -- walked in chunks by RecordingFeeder (ring of pinned
+    staging buffers inside the library: host copy | H2D | transform overlap), Tx consumed on the device (band power
+    per channel and bin, a reduction) so that only [channels, 257] floats leave it.  Wall clock, host to host."""
+    from ssqueeze_rs_b200.batch import RecordingFeeder
+    ch, n = max(1, int(CHANNELS * scale)), SAMPLES
+    win = np.hanning(N_FFT)
+    nfq = N_FFT // 2 + 1
+    x = make_neural(torch, ch, n, FS, dev, 0x5351 + rank)
+    rec = (x / 0.195).clamp_(-32768, 32767).to(torch.int16).t().contiguous().cpu().numpy()  # pageable [n, ch]
+    del x
+    torch.cuda.empty_cache()
+    ph = torch.empty((ch, nfq), dtype=torch.float32, pin_memory=True)
+    chunk = 1 << 15
+    split = {}
+
+    def step():
+        power = torch.zeros((ch, nfq), dtype=torch.float32, device=dev)
+        with torch.cuda.stream(stream):
+            ta = time.perf_counter()
+            feed = RecordingFeeder(eng, rec, win, N_FFT, HOP, FS, chunk=chunk, scale=0.195, depth=3)
+            tb = time.perf_counter()
+            for Tx in feed:
+                power += torch.view_as_real(Tx).square_().sum(dim=(2, 3))
+            ph.copy_(power, non_blocking=True)
+            stream.synchronize()
+            tc = time.perf_counter()
+            feed.close()
+            split.update(setup_ms=(tb - ta) * 1e3, stream_ms=(tc - tb) * 1e3, teardown_ms=(time.perf_counter() - tc) * 1e3)
+
+    step()
+    t0 = time.perf_counter()
+    steps = 2
+    for _ in range(steps):
+        step()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    r = _record("ssq_stft via RecordingFeeder (e2e, int16 host recording)", float(ch) * n, ms, algorithmic_bytes(ch, n),
+                dev, world,
+                f"configs[1] geometry, {ch}ch x {n} int16 interleaved in pageable host memory, chunks of {chunk} samples "
+                f"through ssq_feeder_push (3 pinned slots; stream and feeder created and destroyed inside the timed step), Tx reduced on device to band power [channels, 257]",
+                "ssq_stft512_h32r_kernel<ssq> + deinterleave_kernel (+ torch reduction as the consumer)",
+                {"e2e": {"h2d_bytes_per_step": int(ch * n * 2), "d2h_bytes_per_step": int(ch * nfq * 4),
+                         "note": "wall clock around RecordingFeeder, pageable host in, pinned host out"},
+                 "scaling": "weak", "band_power_checksum": float(ph.sum()),
+                 "split_ms": {k: round(v, 2) for k, v in split.items()}})
+    del rec
+    torch.cuda.empty_cache()
+    return r
+
+
+def side_configs(torch, eng, dev, rank, world, stream, cpu, scale=1.0, only=None):
     g = torch.Generator(device=dev)
     g.manual_seed(0x5351 + rank)
     out = {}
     from ssqueeze_rs_b200.dist import max_over_ranks
     for key, fn in (("c5", side_c5), ("c4_istft", side_c4_istft), ("c3_ssq_cwt", side_c3_ssq_cwt),
-                    ("c2_ridges_e2e", side_ridges_e2e)):
+                    ("c2_ridges_e2e", side_ridges_e2e), ("c2_feeder_e2e", side_feeder_e2e)):
+        if only and key not in only:
+            continue
         r, err = None, None
         try:
             r = fn(torch, eng, dev, rank, world, stream, g, cpu, scale)
@@ -622,7 +675,7 @@ def run_ours(args, rank, world, local_rank):
         del x
         torch.cuda.empty_cache()
         configs = side_configs(torch, eng, dev, rank, world, stream, cpu=(world == 1 and not args.no_cpu_baseline),
-                               scale=args.side_scale)
+                               scale=args.side_scale, only=[k for k in args.only_side.split(",") if k] or None)
 
     if rank == 0:
         line = {
@@ -847,6 +900,7 @@ def main():
     ap.add_argument("--e2e-channels", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the c5 / c4_istft / c3_ssq_cwt sub-records")
+    ap.add_argument("--only-side", default="", help="comma-separated keys of the side records to run (default: all)")
     ap.add_argument("--side-scale", type=float, default=1.0, help="shrink the side configs (channels, c5 length) for smoke runs")
     ap.add_argument("--ref-samples", type=int, default=450_000, help="samples per step of the reference arm")
     ap.add_argument("--n-fft", type=int, default=N_FFT, help="side workloads only: another STFT geometry")

@@ -310,6 +310,18 @@ ssq_status ssq_stream_push_i16(ssq_stream* s, const int16_t* d_chunk, int64_t n_
 ssq_status ssq_stream_push_f32(ssq_stream* s, const float* d_chunk, int64_t n_new, float scale,
                                float* d_Tx, int64_t* frames_written);
 
+/* Host feeder of a stream: the chunk pointer is HOST memory (pageable is fine: a memory-mapped (samples, channels)
+ * .dat / .bin as the reference's scripts read them, tests/stft_ssq_test.py:218-283, tests/stft_test.py:374-377).
+ * dtype 0 = int16, 1 = float32; `depth` (2..8) pinned + device staging slots of max_chunk x channels elements: the
+ * host copy of chunk i+1 overlaps the H2D copy of chunk i and the transform of chunk i-1.  ssq_feeder_push queues the
+ * work and returns; d_Tx (device, as in ssq_stream_push_*) is written in the order of the context's stream.  The
+ * feeder must be destroyed before its stream. */
+typedef struct ssq_feeder ssq_feeder;
+ssq_status ssq_feeder_create(ssq_stream* s, int dtype, int depth, ssq_feeder** out);
+void ssq_feeder_destroy(ssq_feeder* f);
+ssq_status ssq_feeder_push(ssq_feeder* f, const void* h_chunk, int64_t n_new, float scale, float* d_Tx,
+                           int64_t* frames_written);
+
 /* pinned host memory helpers for the host-buffer path */
 ssq_status ssq_host_alloc(void** p, size_t bytes);
 void ssq_host_free(void* p);

@@ -12,6 +12,10 @@ pub struct SsqCtx {
 pub struct SsqStream {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct SsqFeeder {
+    _private: [u8; 0],
+}
 
 pub const SSQ_FLAG_MODULATED: c_uint = 1 << 0;
 pub const SSQ_FLAG_NO_FLIPUD: c_uint = 1 << 1;
@@ -68,6 +72,9 @@ extern "C" {
     pub fn ssq_stream_frames_after(s: *const SsqStream, n_new: i64) -> i64;
     pub fn ssq_stream_push_i16(s: *mut SsqStream, d_chunk: *const i16, n_new: i64, scale: c_float, d_tx: *mut c_float, frames_written: *mut i64) -> c_int;
     pub fn ssq_stream_push_f32(s: *mut SsqStream, d_chunk: *const c_float, n_new: i64, scale: c_float, d_tx: *mut c_float, frames_written: *mut i64) -> c_int;
+    pub fn ssq_feeder_create(s: *mut SsqStream, dtype: c_int, depth: c_int, out: *mut *mut SsqFeeder) -> c_int;
+    pub fn ssq_feeder_destroy(f: *mut SsqFeeder);
+    pub fn ssq_feeder_push(f: *mut SsqFeeder, h_chunk: *const c_void, n_new: i64, scale: c_float, d_tx: *mut c_float, frames_written: *mut i64) -> c_int;
     pub fn ssq_host_alloc(p: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn ssq_host_free(p: *mut c_void);
     pub fn ssq_memcpy_async(dst: *mut c_void, src: *const c_void, bytes: usize, kind: c_int, cuda_stream: *mut c_void) -> c_int;

@@ -307,6 +307,91 @@ class SsqStftStream:
             pass
 
 
+class RecordingFeeder:
+    """Host half of the streaming path: walks an interleaved (samples, channels) recording that lies in HOST memory --
+    a NumPy array or a memory-mapped int16 / float32 file, as the reference's multichannel scripts open them
+    (tests/stft_ssq_test.py:218-283, tests/stft_test.py:374-377) -- in chunks, through the library's ring of pinned
+    staging buffers (ssq_feeder_*: host copy | H2D | transform overlap), and yields the frames of every chunk as they
+    become complete: complex64 CUDA tensors [channels, n_freqs, frames] that stay on the device for a consumer
+    (ridge extraction, band power, a reduction).  Concatenated along frames they equal `Engine.ssq_stft` on the whole
+    recording bit for bit.
+
+        rec = np.memmap("probe.dat", dtype=np.int16, mode="r").reshape(-1, 384)
+        with RecordingFeeder(eng, rec, np.hanning(512), scale=0.195, fs=30000.0) as feed:
+            for Tx in feed:              # [384, 257, frames of this chunk]
+                ...
+    """
+
+    def __init__(self, engine: "Engine", recording, window, n_fft=512, hop_len=32, fs=1.0, chunk=1 << 16, scale=1.0,
+                 padtype="reflect", squeezing="sum", gamma=None, depth=3):
+        rec = recording
+        if rec.ndim != 2:
+            raise ValueError("recording must be [samples, channels]")
+        if rec.dtype not in (np.int16, np.float32):
+            raise ValueError("recording dtype must be int16 or float32")
+        self.eng, self.rec, self.scale = engine, rec, float(scale)
+        self.n_total, self.channels = int(rec.shape[0]), int(rec.shape[1])
+        self.chunk = int(min(max(1, chunk), self.n_total))
+        self.stream = SsqStftStream(engine, self.channels, self.n_total, self.chunk, window, n_fft, hop_len, fs,
+                                    padtype=padtype, squeezing=squeezing, gamma=gamma)
+        h = C.c_void_p()
+        st = load().ssq_feeder_create(self.stream._h, 0 if rec.dtype == np.int16 else 1, int(depth), C.byref(h))
+        raise_status(st, engine.ctx.handle)
+        self._h = h
+        self.pos = 0
+
+    @property
+    def total_frames(self) -> int:
+        return self.stream.total_frames
+
+    def push_next(self):
+        """Queues the next chunk; returns the CUDA tensor of its frames (None at the end of the recording)."""
+        import torch
+        if self.pos >= self.n_total:
+            return None
+        n_new = min(self.chunk, self.n_total - self.pos)
+        src = self.rec[self.pos:self.pos + n_new]
+        if not src.flags["C_CONTIGUOUS"]:
+            src = np.ascontiguousarray(src)
+        frames = max(int(load().ssq_stream_frames_after(self.stream._h, n_new)), 0)
+        # (torch's caching allocator hands the same blocks back once the consumer drops the previous chunks)
+        out = torch.empty((self.channels, self.stream.n_freqs, frames), dtype=torch.complex64, device=self.eng.device)
+        self.eng._bind_stream()
+        fw = C.c_int64()
+        st = load().ssq_feeder_push(self._h, C.c_void_p(src.ctypes.data), n_new, self.scale,
+                                    C.c_void_p(out.data_ptr() if frames > 0 else 0), C.byref(fw))
+        raise_status(st, self.eng.ctx.handle)
+        assert fw.value == frames
+        self.pos += n_new
+        return out
+
+    def __iter__(self):
+        while True:
+            out = self.push_next()
+            if out is None:
+                return
+            yield out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().ssq_feeder_destroy(self._h)
+            self._h = None
+        if getattr(self, "stream", None):
+            self.stream.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def shard_channels(channels: int, n_devices: int):
     """Contiguous channel blocks: device g gets [g*C/G, (g+1)*C/G)."""
     return [(g * channels // n_devices, (g + 1) * channels // n_devices) for g in range(n_devices)]

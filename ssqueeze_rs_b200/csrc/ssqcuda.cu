@@ -1222,6 +1222,118 @@ extern "C" ssq_status ssq_stream_push_f32(ssq_stream* s, const float* d_chunk, i
   return stream_push<float>(s, d_chunk, n_new, scale, d_Tx, frames_written);
 }
 
+// ---------------------------------------------------------------------------
+// Host-side feeder of a stream (the reader half): the recording lies in HOST memory -- typically a
+// memory-mapped (samples, channels) int16 .dat / .bin file as the reference's scripts open them
+// (tests/stft_ssq_test.py:218-283, tests/stft_test.py:374-377), i.e. pageable memory.  A ring of `depth` pinned
+// staging buffers and device chunk buffers decouples the three stages: the host copy (and page-in) of chunk i+1 into
+// its pinned slot runs while chunk i crosses PCIe on a copy stream and chunk i-1 is transformed on the context's
+// stream.  ssq_feeder_push returns as soon as the work is queued; the caller's d_Tx is written in stream order.
+// ---------------------------------------------------------------------------
+struct ssq_feeder {
+  ssq_stream* s = nullptr;
+  int dtype = 0;  // 0 int16, 1 float32
+  int depth = 2;
+  size_t elem = 2, slot_bytes = 0;
+  std::vector<void*> pinned, dev;
+  std::vector<cudaEvent_t> copied, consumed;  // H2D of the slot done / the de-interleave kernel has read the slot
+  std::vector<char> used;
+  cudaStream_t copy_stream = nullptr;
+  int64_t pushes = 0;
+};
+
+extern "C" void ssq_feeder_destroy(ssq_feeder* f) {
+  if (!f) return;
+  if (f->s) cudaSetDevice(f->s->ctx->device);
+  if (f->copy_stream) cudaStreamSynchronize(f->copy_stream);
+  if (f->s) cudaStreamSynchronize(f->s->ctx->stream);
+  for (void* p : f->pinned)
+    if (p) cudaFreeHost(p);
+  for (void* p : f->dev)
+    if (p) cudaFree(p);
+  for (cudaEvent_t e : f->copied)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : f->consumed)
+    if (e) cudaEventDestroy(e);
+  if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
+  delete f;
+}
+
+extern "C" ssq_status ssq_feeder_create(ssq_stream* s, int dtype, int depth, ssq_feeder** out) {
+  if (!s || !out) return ssq_fail(s ? s->ctx : nullptr, SSQ_EINVAL, "ssq_feeder_create: NULL argument");
+  *out = nullptr;
+  ssq_ctx* ctx = s->ctx;
+  if (dtype != 0 && dtype != 1) return ssq_fail(ctx, SSQ_EINVAL, "feeder dtype must be 0 (int16) or 1 (float32)");
+  if (depth < 2) depth = 2;
+  if (depth > 8) depth = 8;
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ssq_feeder* f = new (std::nothrow) ssq_feeder();
+  if (!f) return ssq_fail(ctx, SSQ_ENOMEM, "out of host memory");
+  f->s = s;
+  f->dtype = dtype;
+  f->depth = depth;
+  f->elem = dtype == 0 ? sizeof(int16_t) : sizeof(float);
+  f->slot_bytes = (size_t)s->max_chunk * (size_t)s->channels * f->elem;
+  f->pinned.assign(depth, nullptr);
+  f->dev.assign(depth, nullptr);
+  f->copied.assign(depth, nullptr);
+  f->consumed.assign(depth, nullptr);
+  f->used.assign(depth, 0);
+  cudaError_t e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+    if ((e = cudaHostAlloc(&f->pinned[i], f->slot_bytes, cudaHostAllocDefault)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&f->dev[i], f->slot_bytes)) != cudaSuccess) break;
+    if ((e = cudaEventCreateWithFlags(&f->copied[i], cudaEventDisableTiming)) != cudaSuccess) break;
+    if ((e = cudaEventCreateWithFlags(&f->consumed[i], cudaEventDisableTiming)) != cudaSuccess) break;
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    ssq_feeder_destroy(f);
+    return ssq_fail(ctx, e == cudaErrorMemoryAllocation ? SSQ_ENOMEM : SSQ_ECUDA, "feeder buffers (%d x %zu B): %s", depth,
+                    f->slot_bytes, cudaGetErrorString(e));
+  }
+  *out = f;
+  return SSQ_OK;
+}
+
+extern "C" ssq_status ssq_feeder_push(ssq_feeder* f, const void* h_chunk, int64_t n_new, float scale, float* d_Tx,
+                                      int64_t* frames_written) {
+  if (!f) return ssq_fail(nullptr, SSQ_EINVAL, "feeder is NULL");
+  ssq_stream* s = f->s;
+  ssq_ctx* ctx = s->ctx;
+  if (frames_written) *frames_written = 0;
+  if (n_new < 0 || n_new > s->max_chunk)
+    return ssq_fail(ctx, SSQ_EINVAL, "chunk of %lld samples (max %lld)", (long long)n_new, (long long)s->max_chunk);
+  if (n_new > 0 && !h_chunk) return ssq_fail(ctx, SSQ_EINVAL, "chunk is NULL");
+  SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int slot = (int)(f->pushes % f->depth);
+  const size_t bytes = (size_t)n_new * (size_t)s->channels * f->elem;
+  if (f->used[slot]) {
+    // the pinned slot may be overwritten once its H2D copy has completed, the device slot once the kernel that
+    // read it has run (ordered on the copy stream, no host wait)
+    SSQ_CUDA_TRY(ctx, cudaEventSynchronize(f->copied[slot]));
+    SSQ_CUDA_TRY(ctx, cudaStreamWaitEvent(f->copy_stream, f->consumed[slot], 0));
+  }
+  if (bytes) {
+    // pageable (memory-mapped) source: this is where the file is read; large chunks on several host threads (one
+    // thread copies ~10 GB/s, the GPU consumes int16 samples faster than that)
+    char* dstp = (char*)f->pinned[slot];
+    const char* srcp = (const char*)h_chunk;
+    if (bytes >= ((size_t)8 << 20)) host_parallel_for(bytes, [=](size_t b, size_t e) { memcpy(dstp + b, srcp + b, e - b); });
+    else memcpy(dstp, srcp, bytes);
+    SSQ_CUDA_TRY(ctx, cudaMemcpyAsync(f->dev[slot], f->pinned[slot], bytes, cudaMemcpyHostToDevice, f->copy_stream));
+  }
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(f->copied[slot], f->copy_stream));
+  SSQ_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, f->copied[slot], 0));
+  ssq_status st = f->dtype == 0
+                      ? stream_push<int16_t>(s, (const int16_t*)f->dev[slot], n_new, scale, d_Tx, frames_written)
+                      : stream_push<float>(s, (const float*)f->dev[slot], n_new, scale, d_Tx, frames_written);
+  SSQ_CUDA_TRY(ctx, cudaEventRecord(f->consumed[slot], ctx->stream));
+  f->used[slot] = 1;
+  f->pushes++;
+  return st;
+}
+
 #include "cwt_host.inl"
 #include "stft_rows.inl"
 #include "ridge_host.inl"

@@ -107,3 +107,19 @@ def test_host_only_entry_points_without_a_gpu():
         lib.ssq_cwt_default_scales(n, nv, 0, C.c_void_p(sc.ctypes.data))
         so = O.generate_log_scales(n, nv)
         assert len(so) == ns and np.allclose(sc, so, rtol=1e-13)
+
+
+def test_ssq_stft_batch_argument_validation_without_gpu(built_lib):
+    """The batched drop-in rejects what the scalar call rejects, before anything touches a device."""
+    from ssqueeze_rs_b200 import _rs
+    w = np.hanning(64)
+    with pytest.raises(TypeError):
+        _rs.ssq_stft_batch(np.zeros(100), w)                      # 1-D: that is `ssq_stft`
+    with pytest.raises(TypeError):
+        _rs.ssq_stft_batch(np.zeros((2, 100), dtype=np.int16), w)
+    with pytest.raises(ValueError):
+        _rs.ssq_stft_batch(np.zeros((2, 100)), w, n_fft=32)       # window longer than n_fft (ssq_stft.rs:96-101)
+    with pytest.raises(ValueError):
+        _rs.ssq_stft_batch(np.zeros((2, 100)), w, n_fft=64, win_len=32)
+    with pytest.raises(OverflowError):
+        _rs.ssq_stft_batch(np.zeros((2, 100)), w, hop_len=-1)

@@ -742,3 +742,30 @@ def test_istft_256(hop, N):
         Sx, _ = rs.stft(x, 256, hop, win, "reflect")
         xb = rs.istft(Sx, win, n_fft=256, hop_len=hop, N=N)
         assert np.abs(xb - x).max() < 1e-4 * np.abs(x).max(), hop
+
+
+def test_rs_ssq_stft_batch_equals_the_per_channel_drop_in():
+    """`_rs.ssq_stft_batch` (all channels in one call, complex64 in pinned host memory or on the device) against the
+    reference-shaped scalar call in the loop of tests/stft_ssq_test.py:230-251: same kernel, same bits."""
+    import torch
+    from ssqueeze_rs_b200 import _rs
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((5, 20000)) * 10
+    win = np.hanning(512)
+    Tx, sf = _rs.ssq_stft_batch(x, win, n_fft=512, hop_len=32, fs=30000.0)
+    assert Tx.dtype == np.complex64 and Tx.shape == (5, 257, 625)
+    for c in range(5):
+        Tc, sfc = _rs.ssq_stft(x[c], win, n_fft=512, hop_len=32, fs=30000.0)
+        assert np.array_equal(sf, sfc)
+        assert np.array_equal(Tx[c].astype(np.complex128), Tc)
+    # the pinned result is reusable as `out=`; float32 input; options pass through
+    x32 = x.astype(np.float32)
+    Tx2, _ = _rs.ssq_stft_batch(x32, win, n_fft=512, hop_len=32, fs=30000.0, out=Tx, modulated=True, padtype="zero")
+    assert Tx2 is Tx
+    Tm, _ = _rs.ssq_stft(x32[3].astype(np.float64), win, n_fft=512, hop_len=32, fs=30000.0, modulated=True, padtype="zero")
+    assert np.array_equal(Tx[3].astype(np.complex128), Tm)
+    # Tx kept on the device
+    Td, _ = _rs.ssq_stft_batch(x, win, n_fft=512, hop_len=32, fs=30000.0, device_out=True)
+    assert isinstance(Td, torch.Tensor) and Td.is_cuda
+    T0, _ = _rs.ssq_stft_batch(x, win, n_fft=512, hop_len=32, fs=30000.0)
+    assert np.array_equal(Td.cpu().numpy(), T0)

@@ -65,3 +65,44 @@ def test_stream_hop_larger_than_n_fft_small_chunks():
     _run(30000, 2, [300, 77, 1500], 512, 512 + 17, "i16")
     assert "256" in _run(9000, 4, [100], 256, 256 + 17, "f32")
     _run(5000, 2, [64], 128, 700, "f32")                # generic kernel
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.float32])
+def test_recording_feeder_from_a_memory_mapped_file(tmp_path, dtype):
+    """Host half of the streaming path: a (samples, channels) file on disk, memory-mapped as the reference's scripts do
+    (tests/stft_ssq_test.py:218-283), fed in ragged chunks through the pinned ring; equals the whole-signal transform
+    bit for bit, with more pushes than ring slots (slot reuse) and a last chunk shorter than the others."""
+    import torch
+    from ssqueeze_rs_b200.batch import Engine, RecordingFeeder
+    eng = Engine(0)
+    n_total, channels = 70001, 6
+    rng = np.random.default_rng(11)
+    if dtype == np.int16:
+        rec = rng.integers(-3000, 3000, size=(n_total, channels), dtype=np.int16)
+        scale = 0.195
+    else:
+        rec = (rng.standard_normal((n_total, channels)) * 20).astype(np.float32)
+        scale = 1.0
+    path = tmp_path / "probe.dat"
+    rec.tofile(path)
+    mm = np.memmap(path, dtype=dtype, mode="r").reshape(-1, channels)
+    win = np.hanning(512)
+    x = (rec.astype(np.float32) * np.float32(scale)).T.copy()
+    whole = eng.ssq_stft(torch.from_numpy(x).cuda(), win, 512, 32, 30000.0)
+    with RecordingFeeder(eng, mm, win, 512, 32, 30000.0, chunk=9000, scale=scale, depth=2) as feed:
+        assert feed.total_frames == whole.shape[2]
+        parts = [t.clone() for t in feed]
+    torch.cuda.synchronize()
+    assert len(parts) == 8
+    got = torch.cat(parts, dim=2)
+    assert got.shape == whole.shape
+    assert torch.equal(got, whole), float((got - whole).abs().max())
+
+
+def test_recording_feeder_argument_errors():
+    from ssqueeze_rs_b200.batch import Engine, RecordingFeeder
+    eng = Engine(0)
+    with pytest.raises(ValueError):
+        RecordingFeeder(eng, np.zeros(100, np.int16), np.hanning(512))
+    with pytest.raises(ValueError):
+        RecordingFeeder(eng, np.zeros((100, 2), np.float64), np.hanning(512))
