@@ -377,9 +377,11 @@ static void ssq_cwt_grid(const double* scales, int64_t ns, int64_t n, double dt,
 
 // The last pass can carry the fused epilogue when it is a 7-bit register pass whose outputs of adjacent columns are
 // adjacent (Ns >= 32) and the row fits 32-bit column arithmetic.
-static bool cwt_fused_ok(const ssq_ctx* ctx, const FftPlanHost& pl, int64_t n) {
+static bool cwt_fused_ok(const ssq_ctx* ctx, const FftPlanHost& pl, int64_t n, int64_t ns) {
   if (ctx->opt.no_cwt_fused || ctx->opt.no_fft128 || pl.npass < 2 || pl.log2T != 5) return false;
-  return pl.r[pl.npass - 1] == 7 && pl.log2L - 7 >= 5 && pl.log2L >= 12 && n < ((int64_t)1 << 30);
+  // (the fused epilogue addresses a channel's Tx with signed 32-bit element offsets)
+  return pl.r[pl.npass - 1] == 7 && pl.log2L - 7 >= 5 && pl.log2L >= 12 && n < ((int64_t)1 << 30) &&
+         ns * n < ((int64_t)1 << 31);
 }
 
 extern "C" ssq_status ssq_ssq_cwt_batch_diag_f32(ssq_ctx* ctx, const float* d_x, int64_t channels, int64_t n,
@@ -421,9 +423,9 @@ extern "C" ssq_status ssq_ssq_cwt_batch_diag_f32(ssq_ctx* ctx, const float* d_x,
   S.ns = (int)ns;
   S.n = n;
   S.gate = (float)(g / K);
-  S.gate2 = g < 0.0 ? 0.f : (float)std::min((g / K) * (g / K), 3.0e38);
+  S.gate2f = (float)std::min(std::max(g < 0.0 ? 0.0 : (g / K) * (g / K), 1e-30), 3.0e38);
   S.is_log = is_log;
-  S.f0 = (float)f0;
+  S.f0s = (float)(f0 * inv_step);
   S.inv_step = (float)inv_step;
   S.flipud = (flags & SSQ_FLAG_NO_FLIPUD) ? 0 : 1;
   S.squeezing = squeezing == SSQ_SQUEEZE_LEBESGUE ? SSQ_SQUEEZE_LEBESGUE : SSQ_SQUEEZE_SUM;
@@ -433,13 +435,13 @@ extern "C" ssq_status ssq_ssq_cwt_batch_diag_f32(ssq_ctx* ctx, const float* d_x,
   SSQ_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   SSQ_TRY(cwt_forward(ctx, c, log2L, pl, lo, hi, tw_s, xhat, ws0, ws1));
   SSQ_CUDA_TRY(ctx, cudaMemsetAsync(d_Tx, 0, (size_t)channels * stage, ctx->stream));
-  if (cwt_fused_ok(ctx, pl, n)) {
+  if (cwt_fused_ok(ctx, pl, n, ns)) {
     // one sweep over all (channel, scale) row pairs: the last pass of every pair reassigns straight into Tx
     // the fused epilogue sees the rows before the 1/L of the inverse transform: fold it into K and the gate
     S.Tx = (float2*)d_Tx;
     S.K = (float)(K / (double)L);
     S.gate = (float)(g / K * (double)L);
-    S.gate2 = g < 0.0 ? 0.f : (float)std::min((g / K * (double)L) * (g / K * (double)L), 3.0e38);
+    S.gate2f = (float)std::min(std::max(g < 0.0 ? 0.0 : (g / K * (double)L) * (g / K * (double)L), 1e-30), 3.0e38);
     S.aux_kb = d_kb;
     S.aux_w = d_w;
     if (d_kb) SSQ_CUDA_TRY(ctx, cudaMemsetAsync(d_kb, 0xff, (size_t)channels * ns * n * sizeof(int), ctx->stream));

@@ -28,9 +28,9 @@ struct SsqCwtParams {
   int ns;
   int64_t n;
   float gate;         // gamma / K (in the units of the W handed to ssq_cwt_item): |W| < gate -> skipped
-  float gate2;        // gate^2, clamped to [0, 3e38] (the fast path compares squared magnitudes)
+  float gate2f;       // max(gate^2, 1e-30), at most 3e38: below it (or above 1e30) the exact out-of-line path decides
   int is_log;
-  float f0, inv_step; // lin: (w - f0) * inv_step ; log: (log2 w - f0) * inv_step
+  float f0s, inv_step; // lin: w * inv_step - f0s ; log: log2 w * inv_step - f0s   (f0s = f0 * inv_step)
   int flipud, squeezing;
   float K, leb_val;
   int* aux_kb;        // optional diagnostics, same layout as Tx: destination row per (scale, column), -1 = nothing added
@@ -53,28 +53,37 @@ __device__ __noinline__ float ssq_cwt_w_slow(float2 Wv, float2 Dv, float gate) {
   return fabsf((bb * c - a * d) / ((c * c + d * d) * 6.283185307179586f));
 }
 
-// One (scale, column) item: returns the destination row of Tx, or -1 when nothing is added (gated, w not finite,
-// bin outside the grid: ssq_cwt.rs:29-30, :167-169, :177-179).  w_out: the phase transform (+inf when gated).
-// Wv, Dv may carry any common positive factor (the ratio is scale-free); P.gate is expressed in their units.
-__device__ __forceinline__ int ssq_cwt_item(const SsqCwtParams& P, float2 Wv, float2 Dv, float& w_out) {
+// One (scale, column) item: returns the bin on the ssq grid BEFORE the flip, or -1 when nothing is added (gated, w
+// not finite, bin outside the grid: ssq_cwt.rs:29-30, :167-169, :177-179).  w_out: the phase transform (+inf when
+// gated).  Wv, Dv may carry any common positive factor (the ratio is scale-free); P.gate is expressed in their units.
+// The fused last pass is bound by issue slots and this epilogue was half of its instructions (profiles/README.md):
+// one range test pair (P.gate2f = max(gate^2, 1e-30) from the host), rcp.approx / lg2.approx (one MUFU each; the
+// parity classification carries their error), the grid map as one FMA, round-half-away as a floor conversion.
+__device__ __forceinline__ int ssq_cwt_bin(const SsqCwtParams& P, float2 Wv, float2 Dv, float& w_out) {
   const float c = Wv.x, d = Wv.y;
   const float m2 = fmaf(c, c, d * d);
   float w;
-  if (m2 > 1e-30f && m2 < 1e30f && m2 >= P.gate2) {  // (gate2 = gate^2 clamped into the fp32 range by the host)
+  if (m2 >= P.gate2f && m2 < 1e30f) {
     const float num = fmaf(Dv.y, c, -Dv.x * d);  // Im(dW conj W)
-    w = fabsf(num) * __frcp_rn(m2 * 6.283185307179586f);
+    w = fabsf(num) * rcp_approx(m2 * 6.283185307179586f);
   } else {
     w = ssq_cwt_w_slow(Wv, Dv, P.gate);
   }
   w_out = w;
   if (!(w <= 3.4028235e38f)) return -1;  // gated / inf / NaN skipped (:167-169)
-  const float v = P.is_log ? (log2f(w) - P.f0) * P.inv_step : (w - P.f0) * P.inv_step;
+  // v = (log2 w - f0) * inv_step  resp. (w - f0) * inv_step, as one FMA with f0s = f0 * inv_step
+  float lw;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lw) : "f"(w));  // one MUFU (w is a frequency: never subnormal on the grid)
+  const float v = fmaf(P.is_log ? lw : w, P.inv_step, -P.f0s);
   // f64::round, half away from zero (:176, :187): floor(v + 1/2) for v > -1/2 (values in (-1/2, 0) round to -0 ->
-  // bin 0), anything at or below -1/2 is a negative bin: dropped
-  const float r = floorf(v + 0.5f);
-  if (!(v > -0.5f && r < (float)P.ns)) return -1;  // out of range dropped (:177-179); NaN fails the first test
-  const int bin = (int)r;
-  return P.flipud ? P.ns - 1 - bin : bin;
+  // bin 0), anything at or below -1/2 is a negative bin: dropped; NaN fails the first test
+  const int bin = __float2int_rd(v + 0.5f);
+  if (!(v > -0.5f) || (unsigned)bin >= (unsigned)P.ns) return -1;  // out of range dropped (:177-179)
+  return bin;
+}
+__device__ __forceinline__ int ssq_cwt_item(const SsqCwtParams& P, float2 Wv, float2 Dv, float& w_out) {
+  const int bin = ssq_cwt_bin(P, Wv, Dv, w_out);
+  return bin < 0 ? -1 : (P.flipud ? P.ns - 1 - bin : bin);
 }
 
 // Stand-alone reassignment (the path taken when the last FFT pass cannot carry the fused epilogue): one thread per
@@ -409,6 +418,14 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   const int c = FUSED ? (cfull >> 1) : cfull;       // column inside the CTA
   constexpr int CW = FUSED ? TC / 2 : TC;           // columns per CTA
   if (threadIdx.x < 128) w128[threadIdx.x] = tw_fwd(P, (int64_t)threadIdx.x << (P.log2L - 7));
+  __shared__ float2* s_tch;  // FUSED: base of the channel's Tx (flip folded in) and of the diagnostics row
+  __shared__ size_t s_drow;
+  if (FUSED && threadIdx.x == 128) {
+    const unsigned cs0 = ((unsigned)P.row0 + 2u * blockIdx.y) >> 1;  // channel * ns + scale (rows: channel, scale, which)
+    const unsigned chn0 = cs0 / (unsigned)P.E.ns;
+    s_tch = P.E.Tx + (size_t)chn0 * P.E.ns * P.E.n + (P.E.flipud ? (size_t)(P.E.ns - 1) * P.E.n : (size_t)0);
+    s_drow = (size_t)cs0 * P.E.n;
+  }
   // in-row indices are 32-bit (L <= 2^27, checked on the host): the passes are issue-bound and 64-bit
   // index arithmetic was a fifth of their instructions
   const int L = 1 << P.log2L;
@@ -511,21 +528,21 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   if (P.log2Ns > 0) {
     // inter-pass twiddle W^{kk (g + 8u)} = W^{kk g} (W^{8 kk})^u: two table look-ups, then powers by
     // repeated squaring / short products (every power is at most 4 multiplications deep)
-    const float2 wg = tw_fwd(P, (int64_t)((kk * g) << twshift));
-    float2 p[16];
-    p[1] = tw_fwd(P, (int64_t)((kk * 8) << twshift));
-    p[2] = cmulf(p[1], p[1]);
-    p[4] = cmulf(p[2], p[2]);
-    p[8] = cmulf(p[4], p[4]);
-    p[3] = cmulf(p[2], p[1]);
-    p[5] = cmulf(p[4], p[1]);
-    p[6] = cmulf(p[4], p[2]);
-    p[7] = cmulf(p[4], p[3]);
+    // q[u] = W^{kk g} (W^{8 kk})^u built by doubling (q[u + 2^i] = q[u] p^(2^i)): 3 + 15 complex multiplications
+    // instead of 14 + 15, every factor at most 5 products deep
+    float2 q[16];
+    q[0] = tw_fwd(P, (int64_t)((kk * g) << twshift));
+    const float2 p1 = tw_fwd(P, (int64_t)((kk * 8) << twshift));
+    const float2 p2 = cmulf(p1, p1), p4 = cmulf(p2, p2), p8 = cmulf(p4, p4);
+    q[1] = cmulf(q[0], p1);
+    q[2] = cmulf(q[0], p2);
+    q[3] = cmulf(q[1], p2);
 #pragma unroll
-    for (int u = 9; u < 16; ++u) p[u] = cmulf(p[8], p[u - 8]);
-    v[0] = cmulf(v[0], wg);
+    for (int u = 0; u < 4; ++u) q[4 + u] = cmulf(q[u], p4);
 #pragma unroll
-    for (int u = 1; u < 16; ++u) v[u] = cmulf(v[u], cmulf(p[u], wg));
+    for (int u = 0; u < 8; ++u) q[8 + u] = cmulf(q[u], p8);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = cmulf(v[u], q[u]);
   }
   fft16_fwd(v);  // v[k1] = sum_u x[g + 8u] W_16^{u k1}
   __syncthreads();  // w128 ready
@@ -544,7 +561,9 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   }
   fft8_fwd(a);  // a[k2] = Y[g + 16 k2]
   fft8_fwd(b);  // b[k2] = Y[g + 8 + 16 k2]
-  if (inv) {
+  // (the fused epilogue works on the conjugates as they are: |W|^2 and |Im(dW conj W)| do not change, the value added
+  // to Tx takes the sign with its factor)
+  if (inv && !FUSED) {
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
       a[k2].y = -a[k2].y;
@@ -554,32 +573,43 @@ __global__ void __launch_bounds__(8 * TC) fft128_pass_kernel(const FftPass P) {
   if constexpr (FUSED) {
     // even lane (W row): keeps a = W[k1 = g], receives the dW row's a; odd lane: keeps b = dW[k1 = g + 8], receives
     // the W row's b.  Each lane then owns 8 outputs o = base + (koff + 16 k2) Ns with both values.
-    const unsigned gr = (unsigned)P.row0 + 2u * blockIdx.y;  // the W row; rows are ordered (channel, scale, which)
-    const unsigned cs = gr >> 1;                              // channel * ns + scale
-    const unsigned chn = cs / (unsigned)P.ns;
+    // CTA-uniform constants (a division and 64-bit products: 10 % of the pass when every thread computed them):
+    // thread 0 wrote them before the barrier above
     // (the 1/L of the inverse transform is folded into E.K and E.gate by the host: the phase ratio is scale-free)
     const int base = ((j - kk) << 7) + kk - (int)P.n1;
     const int koff = g + 8 * which_l;
-    float2* Tch = P.E.Tx + (size_t)chn * P.E.ns * P.E.n;
-    const size_t drow = (size_t)cs * P.E.n;  // diagnostics: [channels, ns, n]
+    // row of Tx = flipud ? ns - 1 - bin : bin, as a signed 32-bit element offset from a per-channel base (the host
+    // takes this path only while ns * n < 2^31): one integer multiply-add per item
+    const int rstep = P.E.flipud ? -(int)P.E.n : (int)P.E.n;
+    float2* Tch = s_tch;
+    const size_t drow = s_drow;  // diagnostics: [channels, ns, n]
+    const bool diag = P.E.aux_kb != nullptr || P.E.aux_w != nullptr;
+    const bool leb = P.E.squeezing == SSQ_SQUEEZE_LEBESGUE;
+    const float Kx = P.E.K, Ky = inv ? -P.E.K : P.E.K;
+    int col = base + koff * Ns;
+    const int cstep = 16 * Ns;
 #pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2) {
+    for (int k2 = 0; k2 < 8; ++k2, col += cstep) {
+      // columns outside the unpadded signal (half of a padded row) are dropped before the exchange: the test is
+      // uniform over the warp for the padded lengths of the CWT, a vote keeps it safe in general
+      const bool inside = (unsigned)col < (unsigned)P.E.n;
+      if (!__any_sync(0xffffffffu, inside)) continue;
       const float2 send = which_l ? a[k2] : b[k2];
       float2 recv;
       recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
       recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
-      const float2 Wr = which_l ? recv : a[k2], Dr = which_l ? b[k2] : recv;
-      const int col = base + (koff + 16 * k2) * Ns;
-      if ((unsigned)col >= (unsigned)P.E.n) continue;
-      const float2 Wv = Wr, Dv = Dr;
+      if (!inside) continue;
+      const float2 Wv = which_l ? recv : a[k2], Dv = which_l ? b[k2] : recv;
       float w;
-      const int k = ssq_cwt_item(P.E, Wv, Dv, w);
-      if (P.E.aux_kb) P.E.aux_kb[drow + col] = k;
-      if (P.E.aux_w) P.E.aux_w[drow + col] = w;
-      if (k < 0) continue;
-      float2* t = Tch + (size_t)k * P.E.n + col;
-      if (P.E.squeezing == SSQ_SQUEEZE_LEBESGUE) atomicAdd(&t->x, P.E.leb_val);
-      else atomicAdd(t, make_float2(Wv.x * P.E.K, Wv.y * P.E.K));
+      const int bin = ssq_cwt_bin(P.E, Wv, Dv, w);
+      if (diag) {
+        if (P.E.aux_kb) P.E.aux_kb[drow + col] = bin < 0 ? -1 : (P.E.flipud ? P.E.ns - 1 - bin : bin);
+        if (P.E.aux_w) P.E.aux_w[drow + col] = w;
+      }
+      if (bin < 0) continue;
+      float2* t = Tch + (bin * rstep + col);
+      if (leb) atomicAdd(&t->x, P.E.leb_val);
+      else atomicAdd(t, make_float2(Wv.x * Kx, Wv.y * Ky));
     }
     return;
   }
