@@ -106,3 +106,27 @@ def test_recording_feeder_argument_errors():
         RecordingFeeder(eng, np.zeros(100, np.int16), np.hanning(512))
     with pytest.raises(ValueError):
         RecordingFeeder(eng, np.zeros((100, 2), np.float64), np.hanning(512))
+
+
+def test_recording_feeder_edge_cases():
+    """Fewer pushes than ring slots, a single-sample last chunk, hop > n_fft (samples between frames are dropped), the
+    n_fft 1024 kernel behind the same feeder, and a strided (non-contiguous) view of the recording."""
+    import torch
+    from ssqueeze_rs_b200.batch import Engine, RecordingFeeder
+    eng = Engine(0)
+    rng = np.random.default_rng(3)
+    for n_total, channels, chunk, n_fft, hop, depth in ((5000, 3, 5000, 512, 32, 4), (4097, 2, 4096, 512, 32, 2),
+                                                       (9000, 2, 700, 512, 529, 2), (20000, 3, 3000, 1024, 256, 3)):
+        rec = (rng.standard_normal((n_total, channels)) * 20).astype(np.float32)
+        win = np.hanning(n_fft)
+        whole = eng.ssq_stft(torch.from_numpy(rec.T.copy()).cuda(), win, n_fft, hop, 30000.0)
+        with RecordingFeeder(eng, rec, win, n_fft, hop, 30000.0, chunk=chunk, depth=depth) as feed:
+            got = torch.cat([t.clone() for t in feed], dim=2)
+        torch.cuda.synchronize()
+        assert torch.equal(got, whole), (n_total, channels, chunk, n_fft, hop)
+    wide = (rng.standard_normal((6000, 8)) * 20).astype(np.float32)
+    view = wide[:, ::2]  # every other channel: rows are not contiguous
+    whole = eng.ssq_stft(torch.from_numpy(np.ascontiguousarray(view.T)).cuda(), np.hanning(512), 512, 32, 30000.0)
+    with RecordingFeeder(eng, view, np.hanning(512), 512, 32, 30000.0, chunk=2500) as feed:
+        got = torch.cat([t.clone() for t in feed], dim=2)
+    assert torch.equal(got, whole)
