@@ -307,6 +307,55 @@ class SsqStftStream:
             pass
 
 
+class ParquetRecording:
+    """A (samples, channels) recording stored as parquet columns -- the on-disk format of the reference's real-data
+    scripts (tests/stft_test.py:374-377 read the whole table into memory with pq.read_table(...).to_pandas().values
+    and hand it to dask in chunks of 10^6 samples).  This wrapper reads it batch by batch instead: it has the `shape`,
+    `dtype` and forward slicing `rec[a:b]` that `RecordingFeeder` needs, and returns C-contiguous float32 (or int16)
+    [b - a, channels] blocks; memory stays at one batch.  Slices must advance monotonically (a stream)."""
+
+    ndim = 2
+
+    def __init__(self, path, columns=None, batch_rows=1 << 16):
+        import pyarrow.parquet as pq
+        self._pf = pq.ParquetFile(str(path), memory_map=True)
+        names = [f.name for f in self._pf.schema_arrow]
+        self.columns = list(columns) if columns is not None else names
+        missing = [c for c in self.columns if c not in names]
+        if missing:
+            raise ValueError(f"columns not in the file: {missing}")
+        import pyarrow as pa
+        types = [self._pf.schema_arrow.field(c).type for c in self.columns]
+        self.dtype = np.dtype(np.int16) if all(pa.types.is_int16(t) for t in types) else np.dtype(np.float32)
+        self.shape = (int(self._pf.metadata.num_rows), len(self.columns))
+        self._batch_rows = int(batch_rows)
+        self._it = None
+        self._buf = np.empty((0, self.shape[1]), dtype=self.dtype)
+        self._buf_start = 0  # global row of _buf[0]
+
+    def _more(self):
+        if self._it is None:
+            self._it = self._pf.iter_batches(batch_size=self._batch_rows, columns=self.columns)
+        b = next(self._it)
+        blk = np.empty((b.num_rows, self.shape[1]), dtype=self.dtype)
+        for j, c in enumerate(self.columns):  # column-major on disk -> interleaved rows
+            blk[:, j] = b.column(b.schema.get_field_index(c)).to_numpy(zero_copy_only=False)
+        return blk
+
+    def __getitem__(self, key):
+        if not isinstance(key, slice) or key.step not in (None, 1):
+            raise TypeError("ParquetRecording supports forward slices rec[a:b] only")
+        a, b, _ = key.indices(self.shape[0])
+        if a < self._buf_start:
+            raise ValueError("ParquetRecording is a stream: slices must not go backwards")
+        while self._buf_start + len(self._buf) < b:
+            drop = min(max(a - self._buf_start, 0), len(self._buf))
+            self._buf = np.concatenate([self._buf[drop:], self._more()], axis=0)
+            self._buf_start += drop
+        lo = a - self._buf_start
+        return np.ascontiguousarray(self._buf[lo:lo + (b - a)])
+
+
 class RecordingFeeder:
     """Host half of the streaming path: walks an interleaved (samples, channels) recording that lies in HOST memory --
     a NumPy array or a memory-mapped int16 / float32 file, as the reference's multichannel scripts open them

@@ -123,3 +123,32 @@ def test_ssq_stft_batch_argument_validation_without_gpu(built_lib):
         _rs.ssq_stft_batch(np.zeros((2, 100)), w, n_fft=64, win_len=32)
     with pytest.raises(OverflowError):
         _rs.ssq_stft_batch(np.zeros((2, 100)), w, hop_len=-1)
+
+
+def test_parquet_recording_streams_the_table(tmp_path):
+    """The parquet reader of the streaming path (host only): forward slices of any size equal the table the reference's
+    script would have loaded whole (tests/stft_test.py:374-377), float and int16 columns, a column subset."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from ssqueeze_rs_b200.batch import ParquetRecording
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((10_001, 5))
+    pq.write_table(pa.table({f"ch{j}": data[:, j] for j in range(5)}), tmp_path / "f.parquet", row_group_size=3000)
+    rec = ParquetRecording(tmp_path / "f.parquet", batch_rows=1024)
+    assert rec.shape == (10_001, 5) and rec.dtype == np.float32 and rec.ndim == 2
+    pos, out = 0, []
+    for n in (1, 999, 4096, 17, 10_001):
+        blk = rec[pos:pos + n]
+        assert blk.flags["C_CONTIGUOUS"] and blk.dtype == np.float32
+        out.append(blk)
+        pos = min(pos + n, 10_001)
+    assert np.array_equal(np.concatenate(out), data.astype(np.float32))
+    with pytest.raises(ValueError):
+        rec[0:10]
+    ints = rng.integers(-3000, 3000, size=(5000, 3), dtype=np.int16)
+    pq.write_table(pa.table({f"c{j}": ints[:, j] for j in range(3)}), tmp_path / "i.parquet")
+    rec = ParquetRecording(tmp_path / "i.parquet", columns=["c2", "c0"])
+    assert rec.dtype == np.int16 and rec.shape == (5000, 2)
+    assert np.array_equal(rec[0:5000], ints[:, [2, 0]])
+    with pytest.raises(ValueError):
+        ParquetRecording(tmp_path / "i.parquet", columns=["nope"])

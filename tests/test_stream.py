@@ -130,3 +130,23 @@ def test_recording_feeder_edge_cases():
     with RecordingFeeder(eng, view, np.hanning(512), 512, 32, 30000.0, chunk=2500) as feed:
         got = torch.cat([t.clone() for t in feed], dim=2)
     assert torch.equal(got, whole)
+
+
+def test_recording_feeder_from_parquet(tmp_path):
+    """The reference's on-disk format end to end: parquet columns -> ParquetRecording -> pinned ring -> ssq_stft
+    (n_fft 1024, hop 256 as in tests/stft_test.py:386) equals the transform of the table loaded whole."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    import torch
+    from ssqueeze_rs_b200.batch import Engine, ParquetRecording, RecordingFeeder
+    eng = Engine(0)
+    rng = np.random.default_rng(4)
+    data = (rng.standard_normal((50_000, 4)) * 20).astype(np.float32)
+    pq.write_table(pa.table({f"ch{j}": data[:, j] for j in range(4)}), tmp_path / "rec.parquet", row_group_size=8192)
+    win = np.hanning(1024)
+    whole = eng.ssq_stft(torch.from_numpy(data.T.copy()).cuda(), win, 1024, 256, 24414.0625)
+    rec = ParquetRecording(tmp_path / "rec.parquet", batch_rows=5000)
+    with RecordingFeeder(eng, rec, win, 1024, 256, 24414.0625, chunk=12_000) as feed:
+        got = torch.cat([t.clone() for t in feed], dim=2)
+    torch.cuda.synchronize()
+    assert torch.equal(got, whole)
