@@ -24,7 +24,7 @@ static ssq_status ridge_run(ssq_ctx* ctx, const C2* d_Tf, int64_t channels, int6
   auto smem_bw = [&](int tt) { return ((size_t)2 * F * (tt + 1) + F) * sizeof(T) + 64 * sizeof(int); };
   while (TT > 1 && smem_bw(TT) > (size_t)200 * 1024) TT >>= 1;
   if (smem_bw(TT) > (size_t)200 * 1024) return ssq_fail(ctx, SSQ_EUNSUPPORTED, "extract_ridges: %lld rows do not fit", (long long)F);
-  const size_t smem_fw = ((size_t)F * (TT + 1) + 3 * F) * sizeof(T);
+  const size_t smem_fw = ((((size_t)F * (TT + 1) + 3) & ~(size_t)3) + 3 * (((size_t)F + 3) & ~(size_t)3)) * sizeof(T);
   SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(ridge_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fw));
   SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(ridge_backward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bw(TT)));
   const int threads = (int)std::min<int64_t>(1024, ((F + 31) / 32) * 32);
