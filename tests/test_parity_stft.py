@@ -769,3 +769,18 @@ def test_rs_ssq_stft_batch_equals_the_per_channel_drop_in():
     assert isinstance(Td, torch.Tensor) and Td.is_cuda
     T0, _ = _rs.ssq_stft_batch(x, win, n_fft=512, hop_len=32, fs=30000.0)
     assert np.array_equal(Td.cpu().numpy(), T0)
+
+
+@pytest.mark.parametrize("n,n_fft,hop", [(300, 512, 32), (5000, 500, 7), (4097, 256, 64), (9000, 8192, 1000), (64, 16, 1)])
+def test_rs_ssq_stft_batch_odd_geometries(n, n_fft, hop):
+    """The batched drop-in through every kernel family (signal shorter than the frame, Bluestein lengths, the rows path
+    above 4096 points, tiny frames at hop 1): equal to the scalar drop-in channel by channel."""
+    from ssqueeze_rs_b200 import _rs
+    rng = np.random.default_rng(n + n_fft)
+    x = rng.standard_normal((3, n))
+    win = np.hanning(n_fft)
+    Tx, sf = _rs.ssq_stft_batch(x, win, n_fft=n_fft, hop_len=hop, fs=1000.0)
+    for c in range(3):
+        Tc, sfc = _rs.ssq_stft(x[c], win, n_fft=n_fft, hop_len=hop, fs=1000.0)
+        assert Tx[c].shape == Tc.shape and np.array_equal(sf, sfc)
+        assert np.array_equal(Tx[c].astype(np.complex128), Tc), (n, n_fft, hop, c)
