@@ -652,6 +652,21 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": abytes,
                 "peak_source": peak_src, "kernel": eng.last_kernel_name()}
+    if (N_FFT, HOP) == (512, 32):
+        # what actually binds this kernel: the on-chip pipes, per frame and SM.  Instruction and wavefront
+        # counts are those of the ncu capture profiles/r2/r2m_* of this kernel (979 warp-instructions -- 249 packed
+        # fp32x2, which hold the fp32 pipe two cycles, and 97 scalar fp32 among them -- and 341 shared-memory
+        # wavefronts per frame); the measured figure comes from this run's kernel time and the clock sampled under load.
+        frames = channels * ((n - 1) // HOP + 1)
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk = kms * 1e-3 * mhz * 1e6 * sms / frames
+        roofline["on_chip"] = {
+            "clk_per_frame_per_sm": clk,
+            "floors_clk": {"fp32_pipe": (249 * 2 + 97) / 4.0, "issue_slots": 979 / 4.0, "l1tex_wavefronts": 341.0},
+            "frac_of_binding_floor": 341.0 / clk,
+            "hbm_equivalent_of_fp32_floor_frac": (abytes / (((249 * 2 + 97) / 4.0) * frames / (mhz * 1e6 * sms)) / 1e9) / peak,
+            "source": "profiles/r2/r2m_ssq_stft512_h32r_full.csv (ncu --set full of this kernel)"}
 
     # ---- e2e through the host-buffer C-ABI call --------------------------------
     del Tx
