@@ -1288,9 +1288,10 @@ extern "C" ssq_status ssq_feeder_create(ssq_stream* s, int dtype, int depth, ssq
   }
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
+    const size_t slot_bytes = f->slot_bytes;
     ssq_feeder_destroy(f);
     return ssq_fail(ctx, e == cudaErrorMemoryAllocation ? SSQ_ENOMEM : SSQ_ECUDA, "feeder buffers (%d x %zu B): %s", depth,
-                    f->slot_bytes, cudaGetErrorString(e));
+                    slot_bytes, cudaGetErrorString(e));
   }
   *out = f;
   return SSQ_OK;
@@ -1328,9 +1329,11 @@ extern "C" ssq_status ssq_feeder_push(ssq_feeder* f, const void* h_chunk, int64_
   ssq_status st = f->dtype == 0
                       ? stream_push<int16_t>(s, (const int16_t*)f->dev[slot], n_new, scale, d_Tx, frames_written)
                       : stream_push<float>(s, (const float*)f->dev[slot], n_new, scale, d_Tx, frames_written);
-  SSQ_CUDA_TRY(ctx, cudaEventRecord(f->consumed[slot], ctx->stream));
+  // the slot is marked used whatever the transform returned: its H2D copy is in flight either way
+  const cudaError_t er = cudaEventRecord(f->consumed[slot], ctx->stream);
   f->used[slot] = 1;
   f->pushes++;
+  if (st == SSQ_OK && er != cudaSuccess) return ssq_fail(ctx, SSQ_ECUDA, "cudaEventRecord: %s", cudaGetErrorString(er));
   return st;
 }
 
