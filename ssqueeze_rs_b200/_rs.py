@@ -177,7 +177,6 @@ def ssq_stft_batch(x, window, n_fft=None, win_len=None, hop_len=1, fs=1.0, padty
     g = float(gamma) if gamma is not None else float("nan")
     if device_out:
         import torch
-        from .batch import Engine
         eng = _batch_engine()
         xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(eng.device)
         Tx = eng.ssq_stft(xd, window, nf, hop, float(fs), padtype=_str(padtype, "padtype"),

@@ -1,5 +1,14 @@
-import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+"""Host model of the shared-memory banks in the reassignment of the n_fft 512 kernel: the kernel's step schedule
+(lane, step -> source bin) applied to the oracle's destination bins of the bench signal; wavefronts per 32-bit tag
+access and per 64-bit accumulator access for a candidate index map.  Reproduces ncu's counts of the shipped layout
+(3.14 / 4.75, profiles/r2/r2m_*) -- layouts can be searched here instead of on the GPU.  Test infrastructure: uses
+oracle/."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..")))
 import bench
 from oracle import ssq_oracle as O
 x = bench.make_neural_cpu(1, 120000, bench.FS, 0x5351+7)
