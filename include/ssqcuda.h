@@ -302,6 +302,12 @@ typedef struct ssq_stream ssq_stream;
 ssq_status ssq_stream_create(ssq_ctx* ctx, int64_t channels, int64_t n_total, int64_t max_chunk,
                              const double* window, int64_t win_n, int n_fft, int hop, double fs,
                              int padtype, int squeezing, double gamma, ssq_stream** out);
+/* the same with the transform chosen: mode 0 = ssq_stft (flags: SSQ_FLAG_MODULATED), mode 1 = stft (the dask caller of
+ * tests/stft_test.py:215-271; the window's first n_fft taps as stft.rs:47-78 takes them; fs, squeezing, gamma unused) */
+ssq_status ssq_stream_create_ex(ssq_ctx* ctx, int64_t channels, int64_t n_total, int64_t max_chunk,
+                                const double* window, int64_t win_n, int n_fft, int hop, double fs,
+                                int padtype, int squeezing, double gamma, int mode, unsigned flags,
+                                ssq_stream** out);
 void ssq_stream_destroy(ssq_stream* s);
 int64_t ssq_stream_total_frames(const ssq_stream* s);
 int64_t ssq_stream_frames_after(const ssq_stream* s, int64_t n_new);

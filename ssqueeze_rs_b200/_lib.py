@@ -89,6 +89,8 @@ SIGNATURES = {
                                         c_vp, c_vp]),
     "ssq_stream_create": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int, c_int, c_dbl,
                                   C.POINTER(c_vp)]),
+    "ssq_stream_create_ex": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int, c_int, c_dbl,
+                                     c_int, C.c_uint, C.POINTER(c_vp)]),
     "ssq_stream_destroy": (None, [c_vp]),
     "ssq_stream_total_frames": (c_i64, [c_vp]),
     "ssq_stream_frames_after": (c_i64, [c_vp, c_i64]),

@@ -265,14 +265,19 @@ class SsqStftStream:
     `Engine.ssq_stft` on the whole recording (no re-padding at chunk seams)."""
 
     def __init__(self, engine: "Engine", channels, n_total, max_chunk, window, n_fft=512, hop_len=32, fs=1.0,
-                 padtype="reflect", squeezing="sum", gamma=None):
+                 padtype="reflect", squeezing="sum", gamma=None, transform="ssq_stft", modulated=False):
+        """transform: "ssq_stft" (frames of Tx) or "stft" (frames of Sx: the caller of tests/stft_test.py:215-271)."""
+        if transform not in ("ssq_stft", "stft"):
+            raise ValueError("transform must be 'ssq_stft' or 'stft'")
         self.eng = engine
         self.channels, self.n_freqs = int(channels), int(n_fft) // 2 + 1
         w, wp = _wptr(window)
         h = C.c_void_p()
-        st = load().ssq_stream_create(engine.ctx.handle, int(channels), int(n_total), int(max_chunk), wp, len(w),
-                                      int(n_fft), int(hop_len), float(fs), PAD.get(padtype, 0),
-                                      SQUEEZE.get(squeezing, 0), float("nan") if gamma is None else float(gamma), C.byref(h))
+        st = load().ssq_stream_create_ex(engine.ctx.handle, int(channels), int(n_total), int(max_chunk), wp, len(w),
+                                         int(n_fft), int(hop_len), float(fs), PAD.get(padtype, 0),
+                                         SQUEEZE.get(squeezing, 0), float("nan") if gamma is None else float(gamma),
+                                         1 if transform == "stft" else 0, _lib.FLAG_MODULATED if modulated else 0,
+                                         C.byref(h))
         raise_status(st, engine.ctx.handle)
         self._h = h
 
@@ -372,7 +377,7 @@ class RecordingFeeder:
     """
 
     def __init__(self, engine: "Engine", recording, window, n_fft=512, hop_len=32, fs=1.0, chunk=1 << 16, scale=1.0,
-                 padtype="reflect", squeezing="sum", gamma=None, depth=3):
+                 padtype="reflect", squeezing="sum", gamma=None, depth=3, transform="ssq_stft", modulated=False):
         rec = recording
         if rec.ndim != 2:
             raise ValueError("recording must be [samples, channels]")
@@ -382,7 +387,8 @@ class RecordingFeeder:
         self.n_total, self.channels = int(rec.shape[0]), int(rec.shape[1])
         self.chunk = int(min(max(1, chunk), self.n_total))
         self.stream = SsqStftStream(engine, self.channels, self.n_total, self.chunk, window, n_fft, hop_len, fs,
-                                    padtype=padtype, squeezing=squeezing, gamma=gamma)
+                                    padtype=padtype, squeezing=squeezing, gamma=gamma, transform=transform,
+                                    modulated=modulated)
         h = C.c_void_p()
         st = load().ssq_feeder_create(self.stream._h, 0 if rec.dtype == np.int16 else 1, int(depth), C.byref(h))
         raise_status(st, engine.ctx.handle)

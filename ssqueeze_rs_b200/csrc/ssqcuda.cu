@@ -1047,6 +1047,8 @@ struct ssq_stream {
   int64_t channels, n_total, max_chunk, cap;
   std::vector<double> wfit;
   int n_fft, hop, left, padtype, squeezing;
+  int mode = 0;        // 0 ssq_stft, 1 stft
+  unsigned flags = 0;  // SSQ_FLAG_MODULATED (ssq_stft)
   double fs, gamma;
   int64_t n_frames_total;
   int64_t received = 0;   // samples pushed so far
@@ -1083,13 +1085,22 @@ static int64_t stream_frames_ready(const ssq_stream* s, int64_t received) {
 extern "C" ssq_status ssq_stream_create(ssq_ctx* ctx, int64_t channels, int64_t n_total, int64_t max_chunk,
                                         const double* window, int64_t win_n, int n_fft, int hop, double fs,
                                         int padtype, int squeezing, double gamma, ssq_stream** out) {
+  return ssq_stream_create_ex(ctx, channels, n_total, max_chunk, window, win_n, n_fft, hop, fs, padtype, squeezing, gamma,
+                              0, 0u, out);
+}
+
+extern "C" ssq_status ssq_stream_create_ex(ssq_ctx* ctx, int64_t channels, int64_t n_total, int64_t max_chunk,
+                                           const double* window, int64_t win_n, int n_fft, int hop, double fs,
+                                           int padtype, int squeezing, double gamma, int mode, unsigned flags,
+                                           ssq_stream** out) {
   if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
+  if (mode != 0 && mode != 1) return ssq_fail(ctx, SSQ_EINVAL, "stream mode must be 0 (ssq_stft) or 1 (stft)");
   if (!out || !window || win_n < 1) return ssq_fail(ctx, SSQ_EINVAL, "NULL/empty argument");
   *out = nullptr;
   if (channels < 1 || n_total < 1 || max_chunk < 1) return ssq_fail(ctx, SSQ_EINVAL, "bad channels/n_total/max_chunk");
   if (n_fft <= 0) n_fft = (int)std::min<int64_t>(n_total, 512);
   if (n_fft < 2 || hop < 1) return ssq_fail(ctx, SSQ_EINVAL, "bad n_fft/hop");
-  if (win_n > n_fft)
+  if (mode == 0 && win_n > n_fft)
     return ssq_fail(ctx, SSQ_EINVAL, "Window length %lld cannot be greater than n_fft %d", (long long)win_n, n_fft);
   SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   ssq_stream* s = new (std::nothrow) ssq_stream();
@@ -1098,7 +1109,18 @@ extern "C" ssq_status ssq_stream_create(ssq_ctx* ctx, int64_t channels, int64_t 
   s->channels = channels;
   s->n_total = n_total;
   s->max_chunk = max_chunk;
-  s->wfit = ssqhost::fit_window(window, win_n, n_fft);
+  if (mode == 1) {  // stft takes the first n_fft taps and panics on a shorter window (stft_utils.rs:8, stft.rs:67)
+    if (win_n < n_fft) {
+      delete s;
+      return ssq_fail(ctx, SSQ_EPANIC, "window length %lld < n_fft %d: the reference panics in rustfft (stft_utils.rs:8, stft.rs:67)",
+                      (long long)win_n, n_fft);
+    }
+    s->wfit.assign(window, window + n_fft);
+  } else {
+    s->wfit = ssqhost::fit_window(window, win_n, n_fft);
+  }
+  s->mode = mode;
+  s->flags = mode == 0 ? (flags & SSQ_FLAG_MODULATED) : 0u;
   s->n_fft = n_fft;
   s->hop = hop;
   s->left = ctx->opt.upstream_framing ? n_fft / 2 : (n_fft - 1) / 2;
@@ -1168,7 +1190,7 @@ static ssq_status stream_push(ssq_stream* s, const T* d_chunk, int64_t n_new, fl
   if (count > 0) {
     if (!d_Tx) return ssq_fail(ctx, SSQ_EINVAL, "d_Tx is NULL but %lld frames are ready", (long long)count);
     StftCall c;
-    c.mode = 0;
+    c.mode = s->mode;
     c.d_x = buf;
     c.x_origin = s->origin;
     c.channels = s->channels;
@@ -1177,11 +1199,11 @@ static ssq_status stream_push(ssq_stream* s, const T* d_chunk, int64_t n_new, fl
     c.wfit = s->wfit;
     c.n_fft = s->n_fft;
     c.hop = s->hop;
-    c.fs = s->fs;
+    c.fs = s->mode == 1 ? 1.0 : s->fs;
     c.padtype = s->padtype;
-    c.squeezing = s->squeezing;
-    c.gamma = s->gamma;
-    c.flags = 0;
+    c.squeezing = s->mode == 1 ? SSQ_SQUEEZE_SUM : s->squeezing;
+    c.gamma = s->mode == 1 ? 0.0 : s->gamma;
+    c.flags = s->flags;
     c.d_out = (float2*)d_Tx;
     c.aux_Sx = nullptr;
     c.aux_dSx = nullptr;

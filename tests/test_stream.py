@@ -150,3 +150,31 @@ def test_recording_feeder_from_parquet(tmp_path):
         got = torch.cat([t.clone() for t in feed], dim=2)
     torch.cuda.synchronize()
     assert torch.equal(got, whole)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(512, 32), (1024, 256), (256, 64), (128, 5)])
+def test_stream_stft_mode_and_modulated_ssq(n_fft, hop):
+    """The stft caller of the reference (tests/stft_test.py:215-271) as a stream -- frames of Sx equal to the
+    whole-signal stft bit for bit on every kernel family (hop 32 packs two frames per FFT) -- and the modulated ssq_stft."""
+    import torch
+    from ssqueeze_rs_b200.batch import Engine, RecordingFeeder
+    eng = Engine(0)
+    rng = np.random.default_rng(n_fft + hop)
+    rec = (rng.standard_normal((30_001, 3)) * 20).astype(np.float32)
+    win = np.hanning(n_fft)
+    xd = torch.from_numpy(rec.T.copy()).cuda()
+    whole = eng.stft(xd, win, n_fft, hop)
+    with RecordingFeeder(eng, rec, win, n_fft, hop, chunk=7777, transform="stft") as feed:
+        got = torch.cat([t.clone() for t in feed], dim=2)
+    if n_fft in (256, 512, 1024):
+        # the register kernels put two frames through one FFT in stft mode (z = x_A w + i x_B w): which of a pair a
+        # frame is depends on where the push starts, so the stream equals the whole-signal transform to fp32 rounding
+        # instead of bit for bit (the generic kernel, last case, does not pair: bit-equal)
+        err = float((got - whole).abs().max() / whole.abs().max())
+        assert err < 2e-6, err
+    else:
+        assert torch.equal(got, whole), float((got - whole).abs().max())
+    whole_m = eng.ssq_stft(xd, win, n_fft, hop, 30000.0, modulated=True)
+    with RecordingFeeder(eng, rec, win, n_fft, hop, 30000.0, chunk=7777, modulated=True) as feed:
+        got = torch.cat([t.clone() for t in feed], dim=2)
+    assert torch.equal(got, whole_m)
