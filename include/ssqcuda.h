@@ -289,6 +289,10 @@ ssq_status ssq_ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_t channels,
                                  double fs, int padtype, int squeezing, double gamma,
                                  unsigned flags, float* Tx);
 
+/* the same pipeline for `stft` (stft.rs:12-95): Sx host complex64 [channels, n_fft/2+1, n_frames] */
+ssq_status ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_t channels, int64_t n, const double* window,
+                             int64_t win_n, int n_fft, int hop, int padtype, float* Sx);
+
 /* ---- streaming ssq_stft over chunks of an interleaved recording ------------ */
 /* replaces the dask map_overlap caller of the reference (tests/stft_ssq_test.py:218-283:
  * (samples, channels) chunks with depth n_fft, a per-channel Python loop inside each chunk).

@@ -66,6 +66,7 @@ extern "C" {
     pub fn ssq_extract_ridges_batch(ctx: *mut SsqCtx, d_tf: *const c_void, is_f64: c_int, channels: i64, n_freq: i64, n_time: i64, scales: *const c_double, penalty: c_double, n_ridges: c_int, bw: c_int, transform: c_int, d_ridge_idxs: *mut i32, d_ridge_f: *mut c_void, d_ridge_e: *mut c_void, d_e_all: *mut c_void) -> c_int;
     pub fn ssq_extract_ridges_host(ctx: *mut SsqCtx, tf: *const c_void, is_f64: c_int, n_freq: i64, n_time: i64, scales: *const c_double, penalty: c_double, n_ridges: c_int, bw: c_int, transform: c_int, ridge_idxs: *mut i32, ridge_f: *mut c_void, ridge_e: *mut c_void, e_all: *mut c_void) -> c_int;
     pub fn ssq_ssq_stft_host_f32(ctx: *mut SsqCtx, x: *const c_float, channels: i64, n: i64, window: *const c_double, win_n: i64, n_fft: c_int, hop: c_int, fs: c_double, padtype: c_int, squeezing: c_int, gamma: c_double, flags: c_uint, tx: *mut c_float) -> c_int;
+    pub fn ssq_stft_host_f32(ctx: *mut SsqCtx, x: *const c_float, channels: i64, n: i64, window: *const c_double, win_n: i64, n_fft: c_int, hop: c_int, padtype: c_int, sx: *mut c_float) -> c_int;
     pub fn ssq_stream_create(ctx: *mut SsqCtx, channels: i64, n_total: i64, max_chunk: i64, window: *const c_double, win_n: i64, n_fft: c_int, hop: c_int, fs: c_double, padtype: c_int, squeezing: c_int, gamma: c_double, out: *mut *mut SsqStream) -> c_int;
     pub fn ssq_stream_create_ex(ctx: *mut SsqCtx, channels: i64, n_total: i64, max_chunk: i64, window: *const c_double, win_n: i64, n_fft: c_int, hop: c_int, fs: c_double, padtype: c_int, squeezing: c_int, gamma: c_double, mode: c_int, flags: c_uint, out: *mut *mut SsqStream) -> c_int;
     pub fn ssq_stream_destroy(s: *mut SsqStream);

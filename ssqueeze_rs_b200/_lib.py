@@ -78,6 +78,7 @@ SIGNATURES = {
                                   c_vp, c_vp]),
     "ssq_ssq_cwt_batch_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_dbl, c_int, c_int,
                                       c_int, c_int, c_dbl, c_u32, c_vp, c_vp]),
+    "ssq_stft_host_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "ssq_ssq_stft_host_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int, c_int,
                                       c_dbl, c_u32, c_vp]),
     "ssq_wavelet_morlet": (c_int, [c_int, c_vp, c_i64, c_dbl, c_dbl, c_vp]),

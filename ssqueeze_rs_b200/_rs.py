@@ -25,7 +25,7 @@ from . import _lib
 from ._lib import (FLAG_ADM_EXACT, FLAG_L2_NORM, FLAG_MODULATED, FLAG_NO_FLIPUD, FLAG_RPADDED, FLAG_SIMD_SCALES, PAD, SQUEEZE,
                    default_context, load, raise_status)
 
-__all__ = ["hello_from_bin", "stft", "ssq_stft", "ssq_stft_batch", "pinned_empty", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt", "icwt", "issq_cwt",
+__all__ = ["hello_from_bin", "stft", "stft_batch", "ssq_stft", "ssq_stft_batch", "pinned_empty", "istft", "issq_stft", "cwt", "cwt_simd", "ssq_cwt", "icwt", "issq_cwt",
            "adm_ssq", "extract_ridges", "morlet", "morlet_freq", "morlet_time", "gmw", "gmw_freq", "gmw_time",
            "gmw_center_frequency"]
 
@@ -194,6 +194,46 @@ def ssq_stft_batch(x, window, n_fft=None, win_len=None, hop_len=1, fs=1.0, padty
                                    g, flags, _ptr(out))
     raise_status(st, ctx.handle)
     return out, sf
+
+
+def stft_batch(x, n_fft, hop_length, window, padtype, *, out=None, device_out=False):
+    """`stft` (stft.rs:12-19) for every row of x [channels, n] in one call: (Sx complex64 [channels, n_fft//2+1,
+    n_frames], freqs).  `out` / `device_out` as in `ssq_stft_batch`."""
+    if not isinstance(x, np.ndarray) or x.ndim != 2 or x.dtype not in (np.float64, np.float32):
+        raise TypeError("argument 'x': expected a 2-D numpy.ndarray [channels, n] of float64 or float32")
+    window = _f64_1d(window, "window")
+    n_fft, hop = int(n_fft), int(hop_length)
+    if n_fft < 0 or hop < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    ch, n = x.shape
+    if ch < 1:
+        raise ValueError("x has no channels")
+    lib = load()
+    nfq, nfr = C.c_int64(), C.c_int64()
+    st = lib.ssq_stft_shape(n, n_fft, hop, C.byref(nfq), C.byref(nfr))
+    if st != _lib.SSQ_OK:
+        raise_status(st, None)
+    shape = (ch, nfq.value, nfr.value)
+    # Array1::linspace(0.0, 0.5, n_freqs) (stft.rs:40), as the scalar entry point fills it
+    freqs = np.arange(nfq.value, dtype=np.float64) * (0.5 / (nfq.value - 1) if nfq.value > 1 else 0.0)
+    if nfq.value > 1:
+        freqs[-1] = 0.5
+    if device_out:
+        import torch
+        eng = _batch_engine()
+        xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(eng.device)
+        return eng.stft(xd, window, n_fft, hop, padtype=_str(padtype, "padtype")), freqs
+    x32 = np.ascontiguousarray(x, dtype=np.float32)
+    if out is None:
+        out = pinned_empty(shape, np.complex64)
+    elif not (isinstance(out, np.ndarray) and out.dtype == np.complex64 and out.shape == shape
+              and out.flags["C_CONTIGUOUS"]):
+        raise ValueError(f"out: expected a C-contiguous complex64 array of shape {shape}")
+    ctx = default_context()
+    st = lib.ssq_stft_host_f32(ctx.handle, _ptr(x32), ch, n, _ptr(window), len(window), n_fft, hop,
+                               PAD.get(_str(padtype, "padtype"), 0), _ptr(out))
+    raise_status(st, ctx.handle)
+    return out, freqs
 
 
 _engine = None

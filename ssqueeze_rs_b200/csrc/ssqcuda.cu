@@ -967,9 +967,24 @@ extern "C" ssq_status ssq_issq_stft_f64(ssq_ctx* ctx, const double* Tx, int64_t 
 // host-buffer batched path: chunked over channels, copies overlapped with
 // compute on three streams (H2D | kernel | D2H).
 // ---------------------------------------------------------------------------
+static ssq_status stft_host_pipeline(ssq_ctx* ctx, int mode, const float* x, int64_t channels, int64_t n,
+                                     const double* window, int64_t win_n, int n_fft, int hop, double fs, int padtype,
+                                     int squeezing, double gamma, unsigned flags, float* Tx);
+
 extern "C" ssq_status ssq_ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_t channels, int64_t n,
                                             const double* window, int64_t win_n, int n_fft, int hop, double fs,
                                             int padtype, int squeezing, double gamma, unsigned flags, float* Tx) {
+  return stft_host_pipeline(ctx, 0, x, channels, n, window, win_n, n_fft, hop, fs, padtype, squeezing, gamma, flags, Tx);
+}
+
+extern "C" ssq_status ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_t channels, int64_t n, const double* window,
+                                        int64_t win_n, int n_fft, int hop, int padtype, float* Sx) {
+  return stft_host_pipeline(ctx, 1, x, channels, n, window, win_n, n_fft, hop, 1.0, padtype, SSQ_SQUEEZE_SUM, 0.0, 0u, Sx);
+}
+
+static ssq_status stft_host_pipeline(ssq_ctx* ctx, int mode, const float* x, int64_t channels, int64_t n,
+                                     const double* window, int64_t win_n, int n_fft, int hop, double fs, int padtype,
+                                     int squeezing, double gamma, unsigned flags, float* Tx) {
   if (!ctx) return ssq_fail(nullptr, SSQ_EINVAL, "ctx is NULL");
   if (!x || !Tx || !window) return ssq_fail(ctx, SSQ_EINVAL, "NULL argument");
   SSQ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1008,8 +1023,9 @@ extern "C" ssq_status ssq_ssq_stft_host_f32(ssq_ctx* ctx, const float* x, int64_
     cudaMemcpyAsync(din, x + (size_t)c0 * n, (size_t)cc * in_per_ch, cudaMemcpyHostToDevice, s_in);
     cudaEventRecord(e_in[b], s_in);
     cudaStreamWaitEvent(ctx->stream, e_in[b], 0);
-    st = ssq_ssq_stft_batch_f32(ctx, din, cc, n, n, window, win_n, n_fft, hop, fs, padtype, squeezing, gamma,
-                                flags, (float*)dout);
+    st = mode == 0 ? ssq_ssq_stft_batch_f32(ctx, din, cc, n, n, window, win_n, n_fft, hop, fs, padtype, squeezing, gamma,
+                                            flags, (float*)dout)
+                   : ssq_stft_batch_f32(ctx, din, cc, n, n, window, win_n, n_fft, hop, padtype, (float*)dout);
     if (st != SSQ_OK) break;
     cudaEventRecord(e_k[b], ctx->stream);
     cudaStreamWaitEvent(s_out, e_k[b], 0);

@@ -123,6 +123,10 @@ def test_ssq_stft_batch_argument_validation_without_gpu(built_lib):
         _rs.ssq_stft_batch(np.zeros((2, 100)), w, n_fft=64, win_len=32)
     with pytest.raises(OverflowError):
         _rs.ssq_stft_batch(np.zeros((2, 100)), w, hop_len=-1)
+    with pytest.raises(TypeError):
+        _rs.stft_batch(np.zeros(100), 64, 16, w, "reflect")
+    with pytest.raises(OverflowError):
+        _rs.stft_batch(np.zeros((2, 100)), -64, 16, w, "reflect")
 
 
 def test_parquet_recording_streams_the_table(tmp_path):

@@ -784,3 +784,22 @@ def test_rs_ssq_stft_batch_odd_geometries(n, n_fft, hop):
         Tc, sfc = _rs.ssq_stft(x[c], win, n_fft=n_fft, hop_len=hop, fs=1000.0)
         assert Tx[c].shape == Tc.shape and np.array_equal(sf, sfc)
         assert np.array_equal(Tx[c].astype(np.complex128), Tc), (n, n_fft, hop, c)
+
+
+@pytest.mark.parametrize("n,n_fft,hop", [(20000, 512, 32), (20000, 1024, 256), (5000, 500, 7), (300, 128, 1)])
+def test_rs_stft_batch_equals_the_per_channel_drop_in(n, n_fft, hop):
+    """`_rs.stft_batch` (host pipeline of ssq_stft_host_f32 / Tx on the device) against the scalar `_rs.stft` loop."""
+    from ssqueeze_rs_b200 import _rs
+    rng = np.random.default_rng(n_fft + hop)
+    x = rng.standard_normal((4, n)) * 10
+    win = np.hanning(n_fft)
+    Sx, fr = _rs.stft_batch(x, n_fft, hop, win, "reflect")
+    assert Sx.dtype == np.complex64
+    for c in range(4):
+        Sc, frc = _rs.stft(x[c], n_fft, hop, win, "reflect")
+        assert np.array_equal(fr, frc)
+        assert np.array_equal(Sx[c].astype(np.complex128), Sc), (n, n_fft, hop, c)
+    Sd, _ = _rs.stft_batch(x, n_fft, hop, win, "reflect", device_out=True)
+    assert np.array_equal(Sd.cpu().numpy(), Sx)
+    Sz, _ = _rs.stft_batch(x.astype(np.float32), n_fft, hop, win, "zero", out=Sx)
+    assert Sz is Sx
