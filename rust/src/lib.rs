@@ -20,6 +20,8 @@ fn _rs(py: Python<'_>, m: &Bound<'_, PyModule>) -> PyResult<()> {
     m.add_function(wrap_pyfunction!(hello_from_bin, py)?)?;
     m.add_function(wrap_pyfunction!(spectral::stft, py)?)?;
     m.add_function(wrap_pyfunction!(spectral::ssq_stft, py)?)?;
+    m.add_function(wrap_pyfunction!(spectral::ssq_stft_batch, py)?)?;
+    m.add_function(wrap_pyfunction!(spectral::stft_batch, py)?)?;
     m.add_function(wrap_pyfunction!(spectral::cwt, py)?)?;
     m.add_function(wrap_pyfunction!(spectral::cwt_simd, py)?)?;
     m.add_function(wrap_pyfunction!(spectral::ssq_cwt, py)?)?;

@@ -94,6 +94,79 @@ pub fn ssq_stft<'py>(
     Ok((tx.into_pyarray(py).into_py(py), ssq_freqs.into_pyarray(py).into_py(py)))
 }
 
+/// `ssq_stft` for every row of x [channels, n] in one call (the per-channel Python loop of
+/// tests/stft_ssq_test.py:230-251): complex64 out -- the device computes in fp32 either way, widening to complex128
+/// would double the PCIe time.  Host pipeline H2D | kernel | D2H inside ssq_ssq_stft_host_f32.
+#[pyfunction]
+#[pyo3(signature = (x, window, n_fft=None, hop_len=1, fs=1.0, padtype="reflect", squeezing="sum", gamma=None, modulated=false))]
+pub fn ssq_stft_batch<'py>(
+    py: Python<'py>,
+    x: PyReadonlyArray2<f64>,
+    window: PyReadonlyArray1<f64>,
+    n_fft: Option<usize>,
+    hop_len: usize,
+    fs: f64,
+    padtype: &str,
+    squeezing: &str,
+    gamma: Option<f64>,
+    modulated: bool,
+) -> PyResult<(PyObject, PyObject)> {
+    let xa = x.as_array();
+    let (channels, n) = (xa.shape()[0], xa.shape()[1]);
+    let x32: Vec<f32> = xa.iter().map(|v| *v as f32).collect(); // row-major [channels, n]
+    let w_s = window.as_array().to_owned();
+    let n_fft = n_fft.unwrap_or(n.min(512));
+    if w_s.len() > n_fft {
+        return Err(PyValueError::new_err(format!("Window length {} cannot be greater than n_fft {}", w_s.len(), n_fft)));
+    }
+    let n_freqs = n_fft / 2 + 1;
+    let n_frames = (n - 1) / hop_len + 1;
+    let mut tx = ndarray::Array3::<num_complex::Complex32>::zeros((channels, n_freqs, n_frames));
+    let (pad, sq) = (pad_code(padtype), squeeze_code(squeezing));
+    let flags = if modulated { ffi::SSQ_FLAG_MODULATED } else { 0 };
+    let g = gamma.unwrap_or(f64::NAN);
+    let st = py.allow_threads(|| {
+        ffi::with_ctx(|c| unsafe {
+            ffi::ssq_ssq_stft_host_f32(c, x32.as_ptr(), channels as i64, n as i64, w_s.as_ptr(), w_s.len() as i64,
+                                       n_fft as c_int, hop_len as c_int, fs, pad, sq, g, flags,
+                                       tx.as_mut_ptr() as *mut f32)
+        })
+    });
+    ffi::with_ctx(|c| ffi::check(st, c))?;
+    let ssq_freqs = Array1::<f64>::from_shape_fn(n_freqs, |i| (i as f64) * 0.5 * fs / ((n_freqs as f64) - 1.0)); // :42-54
+    Ok((tx.into_pyarray(py).into_py(py), ssq_freqs.into_pyarray(py).into_py(py)))
+}
+
+/// `stft` for every row of x [channels, n] in one call (ssq_stft_host_f32); complex64 out.
+#[pyfunction]
+pub fn stft_batch<'py>(
+    py: Python<'py>,
+    x: PyReadonlyArray2<f64>,
+    n_fft: usize,
+    hop_length: usize,
+    window: PyReadonlyArray1<f64>,
+    padtype: &str,
+) -> PyResult<(PyObject, PyObject)> {
+    let xa = x.as_array();
+    let (channels, n) = (xa.shape()[0], xa.shape()[1]);
+    let x32: Vec<f32> = xa.iter().map(|v| *v as f32).collect();
+    let w_s = window.as_array().to_owned();
+    let (mut nfq, mut nfr) = (0i64, 0i64);
+    let st = unsafe { ffi::ssq_stft_shape(n as i64, n_fft as c_int, hop_length as c_int, &mut nfq, &mut nfr) };
+    ffi::check(st, std::ptr::null())?;
+    let mut sx = ndarray::Array3::<num_complex::Complex32>::zeros((channels, nfq as usize, nfr as usize));
+    let pad = pad_code(padtype);
+    let st = py.allow_threads(|| {
+        ffi::with_ctx(|c| unsafe {
+            ffi::ssq_stft_host_f32(c, x32.as_ptr(), channels as i64, n as i64, w_s.as_ptr(), w_s.len() as i64,
+                                   n_fft as c_int, hop_length as c_int, pad, sx.as_mut_ptr() as *mut f32)
+        })
+    });
+    ffi::with_ctx(|c| ffi::check(st, c))?;
+    let freqs = Array1::<f64>::linspace(0.0, 0.5, nfq as usize); // stft.rs:40
+    Ok((sx.into_pyarray(py).into_py(py), freqs.into_pyarray(py).into_py(py)))
+}
+
 /// Inverse of `stft` (north star; spec old/ssqueezepy/_stft.py:184-256 in the crate's framing)
 #[pyfunction]
 #[pyo3(signature = (sx, window, n_fft=None, win_len=None, hop_len=1, n=None, win_exp=1))]
