@@ -80,7 +80,7 @@ __device__ __forceinline__ H32RItem h32r_item(const StftParams& P, float txs, fl
     it.vim = 0.f;
   } else {
     it.vre = c * txs;
-    it.vim = __uint_as_float(__float_as_uint(d0 * txs) ^ sgn);
+    it.vim = d0 * __uint_as_float(__float_as_uint(txs) ^ sgn);  // (sign folded into the factor: 10.68 vs 10.70 ms per 128 channels)
   }
   return it;
 }
