@@ -124,6 +124,8 @@ def test_ssq_stft_batch_argument_validation_without_gpu(built_lib):
     with pytest.raises(OverflowError):
         _rs.ssq_stft_batch(np.zeros((2, 100)), w, hop_len=-1)
     with pytest.raises(TypeError):
+        _rs.ssq_cwt_batch(np.zeros(100))
+    with pytest.raises(TypeError):
         _rs.stft_batch(np.zeros(100), 64, 16, w, "reflect")
     with pytest.raises(OverflowError):
         _rs.stft_batch(np.zeros((2, 100)), -64, 16, w, "reflect")

@@ -419,3 +419,28 @@ def test_icwt_two_integral_power_of_two():
                 xo = O.icwt(Wx, wav, sc, one_int=False, x_mean=0.125, x_len=xl)
                 assert xr.shape == xo.shape
                 assert np.abs(xr - xo).max() < 2 * RTOL * np.abs(xo - 0.125).max(), (N, wav, xl)
+
+
+def test_rs_ssq_cwt_batch_against_the_per_channel_drop_in():
+    """`_rs.ssq_cwt_batch` (all channels in one call, complex64 in pinned host memory or on the device) against the
+    scalar `_rs.ssq_cwt` loop: the same kernels; the fused tail adds contributions of different scales in no fixed
+    order, so the comparison is to fp32 rounding of the map's maximum, and the column sums to 1e-6."""
+    import torch
+    from ssqueeze_rs_b200 import _rs
+    rng = np.random.default_rng(8)
+    n = 3000
+    tt = np.arange(n) / 1000.0
+    x = np.stack([np.sin(2 * np.pi * (20 + 10 * c) * tt) + 0.2 * rng.standard_normal(n) for c in range(3)])
+    Tx, sf = _rs.ssq_cwt_batch(x, fs=1000.0, maprange="maximal", nv=16)
+    assert Tx.dtype == np.complex64 and Tx.shape[0] == 3 and Tx.shape[2] == n
+    for c in range(3):
+        Tc, sfc = _rs.ssq_cwt(x[c], fs=1000.0, maprange="maximal", nv=16)
+        assert np.array_equal(sf, sfc) and Tx[c].shape == Tc.shape
+        scale = np.abs(Tc).max()
+        assert np.abs(Tx[c] - Tc).max() <= 2e-5 * scale
+        assert np.abs(Tx[c].sum(0) - Tc.sum(0)).max() <= 1e-5 * np.abs(Tc.sum(0)).max()
+    Td, _ = _rs.ssq_cwt_batch(x.astype(np.float32), fs=1000.0, maprange="maximal", nv=16, device_out=True)
+    assert isinstance(Td, torch.Tensor) and Td.is_cuda
+    assert np.abs(Td.cpu().numpy() - Tx).max() <= 2e-5 * np.abs(Tx).max()
+    T2, _ = _rs.ssq_cwt_batch(x, fs=1000.0, maprange="maximal", nv=16, out=Tx)
+    assert T2 is Tx
