@@ -105,12 +105,18 @@ static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int
     const int R = 1 << P.r, T = 1 << P.log2T;
     dim3 grid((unsigned)(L / ((int64_t)R * T)), (unsigned)rows);
     if (last && base.store_mode == 2) {
-      // fused ssq_cwt epilogue: lane pairs carry the W and dW rows of one scale, 32 columns per CTA of 512 threads
+      // fused ssq_cwt epilogue: lane pairs carry the W and dW rows of one scale; 16 columns per CTA of 256 threads by
+      // default (half the barrier domain of the 512-thread shape: 13.19 vs 13.55 ms per channel on C3), option cwt_fused_tc
       // (cwt_fused_ok guarantees r == 7, log2Ns >= 6 and an even number of rows starting at an even row)
+      if (ctx->opt.cwt_fused_tc == 32) {
+        dim3 g2((unsigned)(L / ((int64_t)128 * 16)), (unsigned)(rows / 2));
+        fft128_pass_kernel<32, true><<<g2, 256, (size_t)32 * 129 * sizeof(float2), ctx->stream>>>(P);
+      } else {
       dim3 g2((unsigned)(L / ((int64_t)128 * 32)), (unsigned)(rows / 2));
       const size_t sm = (size_t)64 * 129 * sizeof(float2);
       SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(fft128_pass_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       fft128_pass_kernel<64, true><<<g2, 512, sm, ctx->stream>>>(P);
+      }
       SSQ_TRY(ssq_check_launch(ctx, "fft128_pass_kernel<fused ssq_cwt>"));
     } else if (P.r == 7 && P.log2T == 5 && (log2Ns == 0 || log2Ns >= 5) && !ctx->opt.no_fft128) {
       // 64 columns per CTA (512 B runs) when the row is long enough; measured faster than 32

@@ -79,7 +79,7 @@ extern "C" ssq_status ssq_ctx_create(int device, ssq_ctx** out) {
   c->stream = c->own_stream;
   // switches: read from the environment once, here (never on the launch path)
   static const char* const names[] = {"no_h32r", "h32r_nw", "no_r1024", "no_r256", "istft_nw", "no_fft128",
-                                      "fft128_tc", "no_cwt_prune", "no_cwt_fused", "cwt_ws_mb", "upstream_framing"};
+                                      "fft128_tc", "no_cwt_prune", "no_cwt_fused", "cwt_fused_tc", "cwt_ws_mb", "upstream_framing"};
   for (const char* nm : names) {
     std::string env = "SSQ_";
     for (const char* q = nm; *q; ++q) env += (char)toupper((unsigned char)*q);
@@ -102,6 +102,7 @@ extern "C" ssq_status ssq_ctx_set_option(ssq_ctx* ctx, const char* name, int64_t
   else if (n == "fft128_tc") o.fft128_tc = value == 32 ? 32 : 64;
   else if (n == "no_cwt_prune") o.no_cwt_prune = value != 0;
   else if (n == "no_cwt_fused") o.no_cwt_fused = value != 0;
+  else if (n == "cwt_fused_tc") o.cwt_fused_tc = value == 32 ? 32 : 64;
   else if (n == "cwt_ws_mb") o.cwt_ws_mb = value > 0 ? value : 0;
   else if (n == "upstream_framing") o.upstream_framing = value != 0;
   else return ssq_fail(ctx, SSQ_EINVAL, "ssq_ctx_set_option: unknown option '%s'", name);
