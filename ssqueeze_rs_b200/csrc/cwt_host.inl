@@ -119,14 +119,19 @@ static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int
       }
       SSQ_TRY(ssq_check_launch(ctx, "fft128_pass_kernel<fused ssq_cwt>"));
     } else if (P.r == 7 && P.log2T == 5 && (log2Ns == 0 || log2Ns >= 5) && !ctx->opt.no_fft128) {
-      // 64 columns per CTA (512 B runs) when the row is long enough; measured faster than 32
+      // columns per CTA (option fft128_tc): 32 by default -- 256-thread CTAs, 256 B runs; the 512-thread shape (64
+      // columns) was the faster one in round 1 and is 8 % (ssq_cwt) to 15 % (cwt) slower now that the passes issue
+      // half the instructions: the barrier domain matters more than the run length
       const int tc_env = ctx->opt.fft128_tc;
-      const int tc = (tc_env == 32 || L < (int64_t)128 * 64 || (log2Ns > 0 && log2Ns < 6)) ? 32 : 64;
+      int tc = (tc_env == 64 && L >= (int64_t)128 * 64 && !(log2Ns > 0 && log2Ns < 6)) ? 64 : 32;
+      if (tc_env == 16 && (log2Ns == 0 || log2Ns >= 4)) tc = 16;
       dim3 g2((unsigned)(L / ((int64_t)128 * tc)), (unsigned)rows);
       const size_t sm = (size_t)tc * 129 * sizeof(float2);
       if (tc == 64) {
         SSQ_CUDA_TRY(ctx, cudaFuncSetAttribute(fft128_pass_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         fft128_pass_kernel<64><<<g2, 512, sm, ctx->stream>>>(P);
+      } else if (tc == 16) {
+        fft128_pass_kernel<16><<<g2, 128, sm, ctx->stream>>>(P);
       } else {
         fft128_pass_kernel<32><<<g2, 256, sm, ctx->stream>>>(P);
       }
