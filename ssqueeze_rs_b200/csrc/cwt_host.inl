@@ -122,9 +122,11 @@ static ssq_status fft_run(ssq_ctx* ctx, const FftPlanHost& pl, FftPass base, int
       // columns per CTA (option fft128_tc): 32 by default -- 256-thread CTAs, 256 B runs; the 512-thread shape (64
       // columns) was the faster one in round 1 and is 8 % (ssq_cwt) to 15 % (cwt) slower now that the passes issue
       // half the instructions: the barrier domain matters more than the run length
-      const int tc_env = ctx->opt.fft128_tc;
+      // (0 = automatic: 16 columns for rows that end in a plain store -- cwt, the STFT rows path: 9.7 vs 10.2 ms per
+      // channel pair of C3 --, 32 for the rows whose last pass is the fused ssq_cwt epilogue: 23.5 vs 24.4 ms)
+      const int tc_env = ctx->opt.fft128_tc ? ctx->opt.fft128_tc : (base.store_mode == 2 ? 32 : 16);
       int tc = (tc_env == 64 && L >= (int64_t)128 * 64 && !(log2Ns > 0 && log2Ns < 6)) ? 64 : 32;
-      if (tc_env == 16 && (log2Ns == 0 || log2Ns >= 4)) tc = 16;
+      if (tc_env == 16 && (log2Ns == 0 || log2Ns >= 4) && L >= (int64_t)128 * 16) tc = 16;
       dim3 g2((unsigned)(L / ((int64_t)128 * tc)), (unsigned)rows);
       const size_t sm = (size_t)tc * 129 * sizeof(float2);
       if (tc == 64) {

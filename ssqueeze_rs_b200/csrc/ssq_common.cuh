@@ -53,7 +53,7 @@ struct ssq_ctx {
   // environment (SSQ_<NAME>) by ssq_ctx_create, changed with ssq_ctx_set_option
   struct Options {
     int no_h32r = 0, h32r_nw = 0, no_r1024 = 0, no_r256 = 0, istft_nw = 8;
-    int no_fft128 = 0, fft128_tc = 32, no_cwt_prune = 0, no_cwt_fused = 0, cwt_fused_tc = 32;
+    int no_fft128 = 0, fft128_tc = 0, no_cwt_prune = 0, no_cwt_fused = 0, cwt_fused_tc = 32;
     int64_t cwt_ws_mb = 0;
     // STFT family framed as upstream ssqueezepy frames it (left pad n_fft / 2, the larger side for even n_fft:
     // old/ssqueezepy/utils/common.py:116-120) instead of the crate's (n_fft - 1) / 2 (stft_utils.rs:22); this one

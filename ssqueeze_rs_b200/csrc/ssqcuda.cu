@@ -99,7 +99,7 @@ extern "C" ssq_status ssq_ctx_set_option(ssq_ctx* ctx, const char* name, int64_t
   else if (n == "no_r256") o.no_r256 = value != 0;
   else if (n == "istft_nw") o.istft_nw = value == 4 ? 4 : 8;
   else if (n == "no_fft128") o.no_fft128 = value != 0;
-  else if (n == "fft128_tc") o.fft128_tc = (value == 16 || value == 64) ? (int)value : 32;
+  else if (n == "fft128_tc") o.fft128_tc = (value == 16 || value == 32 || value == 64) ? (int)value : 0;
   else if (n == "no_cwt_prune") o.no_cwt_prune = value != 0;
   else if (n == "no_cwt_fused") o.no_cwt_fused = value != 0;
   else if (n == "cwt_fused_tc") o.cwt_fused_tc = value == 32 ? 32 : 64;
