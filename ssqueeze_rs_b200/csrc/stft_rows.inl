@@ -1,8 +1,8 @@
 // stft_rows.inl -- STFT family through the batched row passes (included by ssqcuda.cu after cwt_host.inl).
 //
-// The reference takes any n_fft (rustfft: ssq_stft.rs:92,198-199, stft.rs:43-44).  Frames of up to 4096 points that
+// The reference takes any n_fft (rustfft: ssq_stft.rs:92,198-199, stft.rs:43-44).  Frames of up to 1024 points that
 // are powers of two live in one warp's shared memory (stft_generic_kernel) or in registers (the 256 / 512 / 1024
-// kernels); everything else -- n_fft > 4096, and lengths that are not powers of two -- goes through the row FFT of
+// kernels); everything else -- n_fft >= 2048, and lengths that are not powers of two -- goes through the row FFT of
 // the CWT path: a batch of frames is a batch of rows, the first pass windows the samples on the fly (load functor 3),
 // and the generic kernel in rows mode does split, phase transform, reassignment and the coalesced store from the
 // spectra.  Lengths that are not powers of two use Bluestein's identity on rows of M = 2^k >= 2 n_fft - 1:
@@ -44,11 +44,28 @@ static ssq_status rows_bluestein_tables(ssq_ctx* ctx, int N, int64_t M, const fl
   return SSQ_OK;
 }
 
+// Rows of 2^11 / 2^12 points (frames of 2048 / 4096 samples): a radix-128 register pass + one generic pass instead of
+// the single shared-memory pass fft_plan() gives short CWT rows -- with it the rows path beats the warp-per-frame
+// shared-memory kernel from 2048 points on (n_fft 4096, 32 ch x 1.8 M, hop 1024: 17.7 ms in the generic kernel).
+static FftPlanHost fft_plan_rows(int l2) {
+  if (l2 != 11 && l2 != 12) return fft_plan(l2);
+  FftPlanHost p;
+  p.log2L = l2;
+  p.npass = 2;
+  p.r[0] = 7;
+  p.r[1] = l2 - 7;
+  p.log2T = 5;
+  return p;
+}
+// frames the shared-memory kernel keeps: powers of two up to 1024 (the register kernels take 256 / 512 / 1024 before
+// it), other lengths up to 32
+static inline bool stft_rows_skip(bool pow2, int N) { return pow2 ? N <= 1024 : N <= 32; }
+
 static ssq_status stft_rows_run(ssq_ctx* ctx, StftParams P /* by value: per-batch copies */, bool* done) {
   *done = false;
   const int N = P.n_fft;
   const bool pow2 = P.is_pow2;
-  if (pow2 ? N <= 4096 : N <= 32) return SSQ_OK;  // the shared-memory kernel (radix-4/2, or a direct sum for tiny n)
+  if (stft_rows_skip(pow2, N)) return SSQ_OK;  // the shared-memory kernel (radix-4/2, or a direct sum for tiny n)
   int l2 = 0;
   int64_t M = 1;
   while (M < (pow2 ? (int64_t)N : 2 * (int64_t)N - 1)) {
@@ -56,7 +73,7 @@ static ssq_status stft_rows_run(ssq_ctx* ctx, StftParams P /* by value: per-batc
     ++l2;
   }
   if (l2 > 27) return ssq_fail(ctx, SSQ_EUNSUPPORTED, "n_fft=%d: rows of 2^%d points", N, l2);
-  const FftPlanHost pl = fft_plan(l2);
+  const FftPlanHost pl = fft_plan_rows(l2);
   const float2 *lo, *hi;
   int tw_s;
   // (the CWT twiddle cache is keyed by the row length; a CWT call after this one rebuilds it)
@@ -174,7 +191,7 @@ static ssq_status istft_rows_run(ssq_ctx* ctx, IstftParams P, bool* done) {
   *done = false;
   const int N = P.n_fft;
   const bool pow2 = P.is_pow2;
-  if (pow2 ? N <= 4096 : N <= 32) return SSQ_OK;
+  if (stft_rows_skip(pow2, N)) return SSQ_OK;
   int l2 = 0;
   int64_t M = 1;
   while (M < (pow2 ? (int64_t)N : 2 * (int64_t)N - 1)) {
@@ -182,7 +199,7 @@ static ssq_status istft_rows_run(ssq_ctx* ctx, IstftParams P, bool* done) {
     ++l2;
   }
   if (l2 > 27) return ssq_fail(ctx, SSQ_EUNSUPPORTED, "n_fft=%d: rows of 2^%d points", N, l2);
-  const FftPlanHost pl = fft_plan(l2);
+  const FftPlanHost pl = fft_plan_rows(l2);
   const float2 *lo, *hi;
   int tw_s;
   SSQ_TRY(cwt_twiddles(ctx, l2, &lo, &hi, &tw_s));
